@@ -1,0 +1,1176 @@
+// engine.cu -- host orchestration of the GPU KPM engine (the counterpart of kpm::Core,
+// OptimizedHamiltonian, Starter and DefaultCompute: cppcore/src/kpm/*.cpp of the reference).
+//
+// Design (B200-first, not a port):
+//  * the scaled Hamiltonian lives on the device in slot-major ELL; stochastic quantities (DOS,
+//    conductivity, moments) use the *original* site order -- results are permutation invariant and the
+//    lattice order already gives banded, L2-friendly gathers -- while unit-vector quantities (LDOS,
+//    Green's) use a breadth-first relabelling from the source so that the light cone of the recursion is
+//    a row prefix (`SliceMap`) and each step only touches `optimal_size(n)` rows;
+//  * all R vectors of a batch are advanced by ONE fused kernel launch per Chebyshev step; the moments are
+//    produced on the device by the kernel's last block, so a whole recursion is an uninterrupted stream
+//    of launches with a single device->host copy of the finished moments at the end;
+//  * random starters are the reference's own MT19937 stream, generated on the device;
+//  * multi-GPU: vectors are sharded over ranks, one ncclAllReduce of the moment sums at the end.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <dlfcn.h>
+#include <thread>
+
+namespace pbk {
+
+using cf = std::complex<float>;
+
+void cuda_check(cudaError_t err, char const* what, char const* file, int line) {
+    if (err == cudaSuccess) return;
+    char buf[512];
+    std::snprintf(buf, sizeof(buf), "CUDA error '%s' (%s) at %s:%d: %s", cudaGetErrorName(err), cudaGetErrorString(err), file, line, what);
+    throw Error(PBK_CUDA_ERROR, buf);
+}
+
+void DevBuf::alloc(size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    PBK_CUDA(cudaMalloc(&ptr, bytes));
+    size = bytes;
+}
+void DevBuf::release() {
+    if (ptr) { cudaFree(ptr); ptr = nullptr; size = 0; }
+}
+
+static double now_seconds() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template<class F> static void parallel_rows(int64_t n, F fn) {
+    int nt = static_cast<int>(std::thread::hardware_concurrency());
+    if (nt < 1) nt = 1;
+    if (nt > 16) nt = 16;
+    if (n < (1 << 16)) nt = 1;
+    if (nt == 1) { fn(int64_t{0}, n); return; }
+    std::vector<std::thread> threads;
+    int64_t const chunk = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        int64_t const b = t * chunk, e = std::min<int64_t>(n, b + chunk);
+        if (b < e) threads.emplace_back([=] { fn(b, e); });
+    }
+    for (auto& t : threads) t.join();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scale, SliceMap, kernels
+// ------------------------------------------------------------------------------------------------
+Scale::Scale(double min_energy, double max_energy) {  // Bounds.hpp:19-25, float literals on purpose
+    constexpr auto tolerance = 0.01f;
+    a = 0.5f * (max_energy - min_energy) * (1 + tolerance);
+    b = 0.5f * (max_energy + min_energy);
+    if (std::abs(b / a) < 0.01f * tolerance) { b = 0; }
+}
+
+int SliceMap::index(int n, int num_moments) const {  // OptimizedHamiltonian.hpp:67-77
+    int const mid = (num_moments - 1 + dest_offset - src_offset) / 2;
+    int const max = std::min(last_index(), mid + src_offset);
+    if (n < mid) return std::min(max, n + src_offset);
+    return std::min(max, num_moments - 1 - n + dest_offset);
+}
+
+int round_num_moments(int n) {
+    if (n < 2) return 2;
+    while ((n - 2) % 4 != 0) ++n;
+    return n;
+}
+
+static constexpr float pi_f = 3.14159265358979323846f;  // numeric/constant.hpp:8
+static constexpr float kb_f = 8.6173303e-5f;             // numeric/constant.hpp:20
+
+std::vector<double> damping_coefficients(int kernel, double lambda_value, int n) {
+    std::vector<double> g(n);
+    auto const N = static_cast<double>(n);
+    for (int i = 0; i < n; ++i) {
+        auto const k = static_cast<double>(i);
+        if (kernel == PBK_JACKSON) {
+            auto const Np = N + 1;
+            constexpr auto pi = double{pi_f};
+            g[i] = ((Np - k) * std::cos(pi * k / Np) + std::sin(pi * k / Np) / std::tan(pi / Np)) / Np;
+        } else if (kernel == PBK_LORENTZ) {
+            g[i] = std::sinh(lambda_value * (1 - k / N)) / std::sinh(lambda_value);
+        } else {
+            g[i] = 1.0;
+        }
+    }
+    return g;
+}
+
+int kernel_required_num_moments(int kernel, double lambda_value, double scaled_broadening) {
+    double const num = (kernel == PBK_LORENTZ) ? lambda_value : static_cast<double>(pi_f);
+    return round_num_moments(static_cast<int>(num / scaled_broadening) + 1);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Engine
+// ------------------------------------------------------------------------------------------------
+Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg) {
+    if (config.min_energy > config.max_energy) {
+        throw Error(PBK_INVALID_ARGUMENT, "KPM: Invalid energy range specified (min > max).");  // Core.cpp:20-22
+    }
+    if (config.kernel == PBK_LORENTZ && config.lambda_value <= 0) {
+        throw Error(PBK_INVALID_ARGUMENT, "Lorentz kernel: lambda must be positive.");  // Kernel.cpp:25
+    }
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0) {
+        throw Error(PBK_CUDA_ERROR, std::string("pbkpm needs a CUDA device and has no CPU fallback: ")
+                                    + (err != cudaSuccess ? cudaGetErrorString(err) : "no device found"));
+    }
+    if (device < 0 || device >= count) throw Error(PBK_INVALID_ARGUMENT, "invalid CUDA device index");
+    PBK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    PBK_CUDA(cudaGetDeviceProperties(&prop, device));
+    num_sms = prop.multiProcessorCount;
+    PBK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&ev0, &ev1, &ev2, &ev3}) PBK_CUDA(cudaEventCreate(e));
+    counter.alloc(64);
+    PBK_CUDA(cudaMemset(counter.as(), 0, 64));
+    mt_state.alloc(sizeof(uint32_t) * (MT_N + 8));
+}
+
+Engine::~Engine() {
+    cudaSetDevice(device);
+    comm_destroy();
+    for (cudaEvent_t e : {ev0, ev1, ev2, ev3}) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+void Engine::require_hamiltonian() const {
+    if (!has_h) throw Error(PBK_LOGIC_ERROR, "pbkpm: no Hamiltonian has been set");
+}
+
+void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const int32_t* indices, const void* data) {
+    if (dt < 0 || dt > 3) throw Error(PBK_INVALID_ARGUMENT, "invalid dtype");
+    if (n_ <= 0 || !indptr || !indices || !data) throw Error(PBK_INVALID_ARGUMENT, "invalid Hamiltonian arrays");
+    PBK_CUDA(cudaSetDevice(device));
+    dtype = dt;
+    n = n_;
+    int64_t const nnz = indptr[n];
+    h_indptr.assign(indptr, indptr + n + 1);
+    h_indices.assign(indices, indices + nnz);
+    h_data.assign(static_cast<const char*>(data), static_cast<const char*>(data) + nnz * dtype_size(dt));
+    has_h = true;
+    natural = DeviceHamiltonian();
+    optimized = DeviceHamiltonian();
+    unscaled = DeviceHamiltonian();
+    have_bounds = false;
+    lanczos_loops = 0;
+    bounds_seconds = 0;
+    stats = pbk_stats{};
+    if (config.min_energy != config.max_energy) {
+        bounds_min = config.min_energy; bounds_max = config.max_energy;
+        have_bounds = true;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-side construction of the device Hamiltonian: scale (+ BFS relabel) + ELL, then one upload.
+// Semantics follow OptimizedHamiltonian::create_scaled / create_reordered (src/kpm/OptimizedHamiltonian.cpp:55-152)
+// and csr_to_ell (numeric/ellmatrix.hpp:65-82); padding uses value 0 and the row's own index.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template<class T> struct real_of { using type = T; };
+template<class R> struct real_of<std::complex<R>> { using type = R; };
+
+struct HostEll {
+    int k = 0;
+    int64_t pitch = 0;
+    std::vector<char> val;
+    std::vector<int32_t> col;
+};
+
+template<class T>
+HostEll build_ell_host(int64_t n, const int32_t* indptr, const int32_t* indices, const T* data, bool scaled, Scale s,
+                       const int32_t* queue /*new->old or null*/, const int32_t* rmap /*old->new or null*/) {
+    using R = typename real_of<T>::type;
+    R const sa = static_cast<R>(s.a), sb = scaled ? static_cast<R>(s.b) : R{0};
+    R const f = scaled ? R{2} / sa : R{1};
+    bool const reordered = queue != nullptr;
+
+    // ELL width: row length plus one where a diagonal has to be created by the b-offset
+    std::vector<int> kmax_part(64, 0);
+    int kmax = 0;
+    {
+        std::mutex m;
+        parallel_rows(n, [&](int64_t b, int64_t e) {
+            int local = 0;
+            for (int64_t row = b; row < e; ++row) {
+                int cnt = indptr[row + 1] - indptr[row];
+                if (sb != R{0}) {
+                    bool has_diag = false;
+                    for (int p = indptr[row]; p < indptr[row + 1]; ++p) has_diag |= (indices[p] == row);
+                    if (!has_diag) ++cnt;
+                }
+                local = std::max(local, cnt);
+            }
+            std::lock_guard<std::mutex> lk(m);
+            kmax = std::max(kmax, local);
+        });
+    }
+    HostEll ell;
+    ell.k = std::max(kmax, 1);
+    ell.pitch = (n + 31) / 32 * 32;
+    ell.val.assign(static_cast<size_t>(ell.k) * ell.pitch * sizeof(T), 0);
+    ell.col.assign(static_cast<size_t>(ell.k) * ell.pitch, 0);
+    T* val = reinterpret_cast<T*>(ell.val.data());
+    int32_t* col = ell.col.data();
+    int const k = ell.k;
+    int64_t const pitch = ell.pitch;
+
+    parallel_rows(n, [&](int64_t b, int64_t e) {
+        std::vector<std::pair<int32_t, T>> buf;
+        for (int64_t new_row = b; new_row < e; ++new_row) {
+            int64_t const row = reordered ? queue[new_row] : new_row;
+            buf.clear();
+            bool diag_done = (sb == R{0});
+            for (int p = indptr[row]; p < indptr[row + 1]; ++p) {
+                int32_t const c = indices[p];
+                T v = data[p];
+                if (scaled) {
+                    if (c == row && sb != R{0}) {
+                        v = reordered ? v * f - sb * f : (v - sb) * f;  // :124-127 vs :61-66
+                        diag_done = true;
+                    } else {
+                        v = v * f;
+                    }
+                }
+                buf.emplace_back(reordered ? rmap[c] : c, v);
+            }
+            if (!diag_done) buf.emplace_back(static_cast<int32_t>(new_row), reordered ? T{-sb * f} : (T{0} - T{sb}) * f);
+            std::sort(buf.begin(), buf.end(), [](auto const& l, auto const& r) { return l.first < r.first; });
+            int sidx = 0;
+            for (auto const& en : buf) { val[sidx * pitch + new_row] = en.second; col[sidx * pitch + new_row] = en.first; ++sidx; }
+            for (; sidx < k; ++sidx) col[sidx * pitch + new_row] = static_cast<int32_t>(new_row);
+        }
+        (void)k;
+    });
+    for (int sidx = 0; sidx < k; ++sidx) for (int64_t r = n; r < pitch; ++r) col[sidx * pitch + r] = 0;
+    return ell;
+}
+
+} // anonymous namespace
+
+void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, bool reorder, Indices const& target) {
+    require_hamiltonian();
+    PBK_CUDA(cudaSetDevice(device));
+    double const t0 = now_seconds();
+    Scale const s = scaled ? scaling_factors() : Scale();
+    dh = DeviceHamiltonian();
+
+    std::vector<int32_t> queue;
+    if (reorder) {
+        // BFS relabelling from src[0]; slice k = the k-th shell (OptimizedHamiltonian.cpp:88-143)
+        queue.reserve(n);
+        queue.push_back(target.src[0]);
+        dh.reorder_map.assign(n, -1);
+        dh.reorder_map[target.src[0]] = 0;
+        std::vector<int32_t> borders{1};
+        for (int64_t h2_row = 0; h2_row < n; ++h2_row) {
+            if (h2_row >= static_cast<int64_t>(queue.size())) {
+                throw Error(PBK_RUNTIME_ERROR, "KPM: the Hamiltonian graph is not connected; the optimal_size "
+                                               "reordering needs a connected system");
+            }
+            int32_t const row = queue[h2_row];
+            for (int p = h_indptr[row]; p < h_indptr[row + 1]; ++p) {
+                int32_t const c = h_indices[p];
+                if (dh.reorder_map[c] < 0) { dh.reorder_map[c] = static_cast<int32_t>(queue.size()); queue.push_back(c); }
+            }
+            if (h2_row == borders.back() - 1) borders.push_back(static_cast<int32_t>(queue.size()));
+        }
+        borders.pop_back();
+        for (int32_t i : target.src) dh.idx.src.push_back(dh.reorder_map[i]);
+        for (int32_t i : target.dest) dh.idx.dest.push_back(dh.reorder_map[i]);
+        auto find_offset = [&](std::vector<int32_t> const& v) {
+            int32_t const mx = *std::max_element(v.begin(), v.end());
+            auto const it = std::find_if(borders.begin(), borders.end(), [&](int32_t b) { return b > mx; });
+            return static_cast<int>(it - borders.begin());
+        };
+        dh.map.src_offset = find_offset(dh.idx.src);
+        dh.map.dest_offset = find_offset(dh.idx.dest);
+        dh.map.data = std::move(borders);
+        dh.reordered = true;
+    } else {
+        dh.idx = target;
+        dh.map.data = {static_cast<int32_t>(n)};
+    }
+
+    HostEll ell;
+    const int32_t* q = reorder ? queue.data() : nullptr;
+    const int32_t* rm = reorder ? dh.reorder_map.data() : nullptr;
+    switch (dtype) {
+        case F32: ell = build_ell_host<float>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const float*>(h_data.data()), scaled, s, q, rm); break;
+        case C64: ell = build_ell_host<cf>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cf*>(h_data.data()), scaled, s, q, rm); break;
+        case F64: ell = build_ell_host<double>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const double*>(h_data.data()), scaled, s, q, rm); break;
+        default: ell = build_ell_host<cd>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cd*>(h_data.data()), scaled, s, q, rm); break;
+    }
+    dh.val.alloc(ell.val.size());
+    dh.col.alloc(ell.col.size() * sizeof(int32_t));
+    PBK_CUDA(cudaMemcpyAsync(dh.val.as(), ell.val.data(), ell.val.size(), cudaMemcpyHostToDevice, stream));
+    PBK_CUDA(cudaMemcpyAsync(dh.col.as(), ell.col.data(), ell.col.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    stats.h2d_bytes += static_cast<int64_t>(ell.val.size() + ell.col.size() * sizeof(int32_t));
+    if (reorder) {
+        dh.perm.alloc(sizeof(int32_t) * n);
+        PBK_CUDA(cudaMemcpyAsync(dh.perm.as(), dh.reorder_map.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream));
+        stats.h2d_bytes += static_cast<int64_t>(sizeof(int32_t) * n);
+    }
+    PBK_CUDA(cudaStreamSynchronize(stream));
+    dh.ell.val = dh.val.as();
+    dh.ell.col = dh.col.as<int32_t>();
+    dh.ell.rows = n;
+    dh.ell.pitch = ell.pitch;
+    dh.ell.k = ell.k;
+    dh.original_idx = target;
+    dh.valid = true;
+    dh.seconds = now_seconds() - t0;
+}
+
+DeviceHamiltonian& Engine::natural_hamiltonian() {
+    if (!natural.valid) build_device_hamiltonian(natural, true, false, Indices{{0}, {0}});
+    return natural;
+}
+
+DeviceHamiltonian& Engine::optimized_for(Indices const& target) {
+    if (!config.optimal_size) {  // no light-cone slicing requested: the natural order serves every index
+        auto& h = natural_hamiltonian();
+        h.idx = target;
+        return h;
+    }
+    if (!(optimized.valid && optimized.original_idx == target)) {  // OptimizedHamiltonian.cpp:43-45
+        optimized = DeviceHamiltonian();
+        build_device_hamiltonian(optimized, true, true, target);
+    }
+    return optimized;
+}
+
+DeviceHamiltonian& Engine::unscaled_hamiltonian() {
+    if (!unscaled.valid) build_device_hamiltonian(unscaled, false, false, Indices{{0}, {0}});
+    return unscaled;
+}
+
+/// velocity operator V_ij = H_ij * (pos_i - pos_j) on the unscaled H (src/kpm/Moments.cpp:132-156)
+void Engine::upload_operator(DeviceHamiltonian& dh, const float* pos) {
+    int64_t const nnz = h_indptr[n];
+    std::vector<char> data(static_cast<size_t>(nnz) * dtype_size(dtype));
+    auto fill = [&](auto* out, auto const* in) {
+        using T = std::remove_pointer_t<decltype(out)>;
+        parallel_rows(n, [&](int64_t b, int64_t e) {
+            for (int64_t row = b; row < e; ++row)
+                for (int p = h_indptr[row]; p < h_indptr[row + 1]; ++p)
+                    out[p] = in[p] * static_cast<T>(pos[row] - pos[h_indices[p]]);
+        });
+    };
+    switch (dtype) {
+        case F32: fill(reinterpret_cast<float*>(data.data()), reinterpret_cast<const float*>(h_data.data())); break;
+        case C64: fill(reinterpret_cast<cf*>(data.data()), reinterpret_cast<const cf*>(h_data.data())); break;
+        case F64: fill(reinterpret_cast<double*>(data.data()), reinterpret_cast<const double*>(h_data.data())); break;
+        default: fill(reinterpret_cast<cd*>(data.data()), reinterpret_cast<const cd*>(h_data.data())); break;
+    }
+    HostEll ell;
+    switch (dtype) {
+        case F32: ell = build_ell_host<float>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const float*>(data.data()), false, Scale(), nullptr, nullptr); break;
+        case C64: ell = build_ell_host<cf>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cf*>(data.data()), false, Scale(), nullptr, nullptr); break;
+        case F64: ell = build_ell_host<double>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const double*>(data.data()), false, Scale(), nullptr, nullptr); break;
+        default: ell = build_ell_host<cd>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cd*>(data.data()), false, Scale(), nullptr, nullptr); break;
+    }
+    dh = DeviceHamiltonian();
+    dh.val.alloc(ell.val.size());
+    dh.col.alloc(ell.col.size() * sizeof(int32_t));
+    PBK_CUDA(cudaMemcpy(dh.val.as(), ell.val.data(), ell.val.size(), cudaMemcpyHostToDevice));
+    PBK_CUDA(cudaMemcpy(dh.col.as(), ell.col.data(), ell.col.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    stats.h2d_bytes += static_cast<int64_t>(ell.val.size() + ell.col.size() * sizeof(int32_t));
+    dh.ell = EllDev{dh.val.as(), dh.col.as<int32_t>(), n, ell.pitch, ell.k};
+    dh.map.data = {static_cast<int32_t>(n)};
+    dh.valid = true;
+}
+
+/// generic operator of KPM.moments(op=...): c128 CSR cast to the Hamiltonian's scalar type (force_cast)
+void Engine::upload_csr_operator(DeviceHamiltonian& dh, int64_t rows, const int32_t* indptr, const int32_t* indices, const cd* data) {
+    int64_t const nnz = indptr[rows];
+    HostEll ell;
+    switch (dtype) {
+        case F32: { std::vector<float> d(nnz); for (int64_t i = 0; i < nnz; ++i) d[i] = static_cast<float>(data[i].real());
+                    ell = build_ell_host<float>(rows, indptr, indices, d.data(), false, Scale(), nullptr, nullptr); break; }
+        case C64: { std::vector<cf> d(nnz); for (int64_t i = 0; i < nnz; ++i) d[i] = cf(static_cast<float>(data[i].real()), static_cast<float>(data[i].imag()));
+                    ell = build_ell_host<cf>(rows, indptr, indices, d.data(), false, Scale(), nullptr, nullptr); break; }
+        case F64: { std::vector<double> d(nnz); for (int64_t i = 0; i < nnz; ++i) d[i] = data[i].real();
+                    ell = build_ell_host<double>(rows, indptr, indices, d.data(), false, Scale(), nullptr, nullptr); break; }
+        default: ell = build_ell_host<cd>(rows, indptr, indices, data, false, Scale(), nullptr, nullptr); break;
+    }
+    dh = DeviceHamiltonian();
+    dh.val.alloc(ell.val.size());
+    dh.col.alloc(ell.col.size() * sizeof(int32_t));
+    PBK_CUDA(cudaMemcpy(dh.val.as(), ell.val.data(), ell.val.size(), cudaMemcpyHostToDevice));
+    PBK_CUDA(cudaMemcpy(dh.col.as(), ell.col.data(), ell.col.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    stats.h2d_bytes += static_cast<int64_t>(ell.val.size() + ell.col.size() * sizeof(int32_t));
+    dh.ell = EllDev{dh.val.as(), dh.col.as<int32_t>(), rows, ell.pitch, ell.k};
+    dh.map.data = {static_cast<int32_t>(rows)};
+    dh.valid = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bounds: Lanczos on the device (compute/lanczos.hpp:101-154); the tiny tridiagonal problem stays on the host
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+/// extreme eigenvalues of the symmetric tridiagonal (alpha, beta) by Sturm-sequence bisection
+void tridiagonal_minmax(std::vector<double> const& alpha, std::vector<double> const& beta, double* mn, double* mx) {
+    int const m = static_cast<int>(alpha.size());
+    double lo = alpha[0], hi = alpha[0];
+    for (int i = 0; i < m; ++i) {
+        double const r = (i > 0 ? std::abs(beta[i - 1]) : 0.0) + (i + 1 < m ? std::abs(beta[i]) : 0.0);
+        lo = std::min(lo, alpha[i] - r);
+        hi = std::max(hi, alpha[i] + r);
+    }
+    auto count_below = [&](double x) {  // number of eigenvalues < x
+        int cnt = 0;
+        double q = alpha[0] - x;
+        if (q < 0) ++cnt;
+        for (int i = 1; i < m; ++i) {
+            double const d = (q == 0.0) ? 1e-300 : q;
+            q = alpha[i] - x - beta[i - 1] * beta[i - 1] / d;
+            if (q < 0) ++cnt;
+        }
+        return cnt;
+    };
+    auto kth = [&](int k) {  // k-th smallest eigenvalue (0-based)
+        double a = lo, b = hi;
+        for (int it = 0; it < 200 && b - a > 1e-15 * std::max(1.0, std::abs(a) + std::abs(b)); ++it) {
+            double const mid = 0.5 * (a + b);
+            if (count_below(mid) > k) b = mid; else a = mid;
+        }
+        return 0.5 * (a + b);
+    };
+    *mn = kth(0);
+    *mx = kth(m - 1);
+}
+
+} // anonymous namespace
+
+cudaError_t launch_uniform_transform(int dtype, const uint32_t* raw, int64_t n, void* dst, cudaStream_t s);
+
+void Engine::compute_bounds() {
+    if (have_bounds) return;
+    require_hamiltonian();
+    PBK_CUDA(cudaSetDevice(device));
+    double const t0 = now_seconds();
+    auto& h = unscaled_hamiltonian();
+    size_t const vbytes = static_cast<size_t>(n) * dtype_size(dtype);
+    DevBuf v0(vbytes), v1(vbytes), t(vbytes);
+    int const w = dtype_words(dtype);
+    raw.ensure(sizeof(uint32_t) * n * w);
+    ensure_moment_buffers(1, 4);
+    double* scal = mom.as<double>();  // [0..1]: <t|v1>, [2]: |v0|^2, [4]: |v1|^2
+    scratch.ensure(sizeof(double) * 2 * num_sms * 8);
+
+    // start vector: default-seeded uniform [0, 1) reals, normalised (lanczos.hpp:105-107)
+    PBK_CUDA(launch_mt_seed(mt_state.as<uint32_t>(), stream));
+    PBK_CUDA(launch_mt_generate(mt_state.as<uint32_t>(), raw.as<uint32_t>(), n * w, stream));
+    PBK_CUDA(launch_uniform_transform(dtype, raw.as<uint32_t>(), n, v1.as(), stream));
+    PBK_CUDA(cudaMemsetAsync(v0.as(), 0, vbytes, stream));
+    PBK_CUDA(launch_dot_moment(dtype, v1.as(), v1.as(), n, scal, 2, 1.0, scratch.as<double>(), counter.as<unsigned>(), num_sms, stream));
+    PBK_CUDA(launch_scale_inv_sqrt(dtype, n, v1.as(), scal + 4, stream));
+
+    std::vector<double> alpha, beta;
+    double previous_min = std::numeric_limits<double>::max();
+    double previous_max = std::numeric_limits<double>::lowest();
+    double const precision = static_cast<double>(config.lanczos_precision) / 100;
+    void* p0 = v0.as();
+    void* p1 = v1.as();
+    for (int i = 0; i < 1000; ++i) {
+        double const b_prev = beta.empty() ? 0.0 : beta.back();
+        StepArgs a;
+        a.h = h.ell; a.x = p1; a.y = t.as(); a.nrows = n; a.R = 1; a.subtract = false; a.scale = 1.0;
+        PBK_CUDA(launch_step(dtype, a, num_sms, stream, nullptr));
+        PBK_CUDA(launch_dot_moment(dtype, t.as(), p1, n, scal, 0, 1.0, scratch.as<double>(), counter.as<unsigned>(), num_sms, stream));
+        PBK_CUDA(launch_lanczos_update(dtype, n, t.as(), p1, p0, b_prev, scal, scal + 2, scratch.as<double>(), counter.as<unsigned>(), num_sms, stream));
+        PBK_CUDA(launch_scale_inv_sqrt(dtype, n, p0, scal + 2, stream));
+        double host[3];
+        PBK_CUDA(cudaMemcpyAsync(host, scal, sizeof(host), cudaMemcpyDeviceToHost, stream));
+        PBK_CUDA(cudaStreamSynchronize(stream));
+        std::swap(p0, p1);
+        alpha.push_back(host[0]);
+        beta.push_back(std::sqrt(host[2]));
+
+        double mn, mx;
+        tridiagonal_minmax(alpha, beta, &mn, &mx);
+        bool const conv_min = std::abs((previous_min - mn) / mn) < precision;
+        bool const conv_max = std::abs((previous_max - mx) / mx) < precision;
+        if (conv_min && conv_max) {
+            bounds_min = mn; bounds_max = mx; lanczos_loops = i;
+            have_bounds = true;
+            bounds_seconds = now_seconds() - t0;
+            return;
+        }
+        previous_min = mn; previous_max = mx;
+    }
+    throw Error(PBK_RUNTIME_ERROR, "Lanczos algorithm did not converge for the min/max eigenvalues.");
+}
+
+void Engine::bounds(double* mn, double* mx, int32_t* loops) {
+    compute_bounds();
+    *mn = bounds_min; *mx = bounds_max; *loops = lanczos_loops;
+}
+
+Scale Engine::scaling_factors() {
+    compute_bounds();
+    return Scale(bounds_min, bounds_max);
+}
+
+int Engine::required_num_moments(double broadening) {
+    auto const s = scaling_factors();
+    return kernel_required_num_moments(config.kernel, config.lambda_value, broadening / s.a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Recursion drivers
+// ------------------------------------------------------------------------------------------------
+int Engine::lane_pad(int R) const {
+    if (R == 1) return 1;
+    int const vmax = 16 / dtype_size(dtype);
+    return (R + vmax - 1) / vmax * vmax;
+}
+
+int Engine::pick_batch(int vectors, int extra_blocks) const {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    // vec_a / vec_b (+ extra) blocks and the raw random words of one lane
+    double const per_lane = static_cast<double>(n) * (dtype_size(dtype) * (2 + extra_blocks) + 4 * dtype_words(dtype));
+    double const reusable = static_cast<double>(vec_a.bytes() + vec_b.bytes() + raw.bytes());
+    int cap = static_cast<int>((0.85 * static_cast<double>(free_b) + reusable) / per_lane);
+    int const hard = 4096 / dtype_size(dtype);  // 256 chunks of 16 bytes per row
+    cap = std::min(cap, hard);
+    cap = std::min(cap, config.max_batch > 0 ? config.max_batch : 64);
+    if (cap < 1) throw Error(PBK_RUNTIME_ERROR, "pbkpm: not enough device memory for one KPM vector pair");
+    int const nb = (vectors + cap - 1) / cap;
+    int rb = (vectors + nb - 1) / nb;
+    rb = std::min(lane_pad(rb), std::max(cap, 1));
+    return std::max(rb, 1);
+}
+
+void Engine::ensure_moment_buffers(int R, int M) {
+    mom.ensure(sizeof(double) * 2 * static_cast<size_t>(R) * M + 64);
+    m01.ensure(sizeof(double) * 3 * R + 64);
+    acc.ensure(sizeof(double) * 2 * M + 64);
+    partials.ensure(sizeof(double) * 3 * static_cast<size_t>(R) * max_step_blocks(num_sms));
+    scratch.ensure(sizeof(double) * 2 * num_sms * 8);
+}
+
+void Engine::step(DeviceHamiltonian const& h, const void* x, void* y, void* y2, int64_t nrows, int R, bool subtract, bool sums,
+                  double scale, int M, int nstep, int fin) {
+    StepArgs a;
+    a.h = h.ell; a.x = x; a.y = y; a.y2 = y2; a.nrows = nrows; a.R = R; a.subtract = subtract; a.sums = sums; a.scale = scale;
+    a.partials = partials.as<double>(); a.counter = counter.as<unsigned>(); a.mom = mom.as<double>(); a.m01 = m01.as<double>();
+    a.M = M; a.n = nstep; a.fin = fin;
+    PBK_CUDA(launch_step(dtype, a, num_sms, stream, nullptr));
+    ++launches;
+    ++stats.step_launches;
+    int const s = dtype_size(dtype);
+    stats.step_bytes += static_cast<double>(nrows) * (h.ell.k * (s + 4.0) + static_cast<double>(R) * s * (2 + (subtract ? 1 : 0) + (y2 ? 1 : 0)));
+}
+
+void Engine::run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_size) {
+    void* r0 = vec_a.as();
+    void* r1 = vec_b.as();
+    PBK_CUDA(cudaEventRecord(ev2, stream));
+    // r1 = 0.5 * H2 * r0, m0 = 0.5 |r0|^2, m1 = <r1|r0>     (make_r1 + collect.initial)
+    int64_t init_rows = n;
+    if (opt_size) {
+        PBK_CUDA(cudaMemsetAsync(r1, 0, static_cast<size_t>(n) * R * dtype_size(dtype), stream));
+        init_rows = h.map.data[std::min(h.map.last_index(), h.map.src_offset + 1)];
+    }
+    step(h, r0, r1, nullptr, init_rows, R, false, true, 0.5, M, 0, FIN_INIT);
+    for (int k = 2; k <= M / 2; ++k) {  // calc_moments::basic (diagonal), calc_moments.hpp:36-51
+        int64_t const rows = opt_size ? h.map.optimal_size(k, M) : n;
+        step(h, r1, r0, nullptr, rows, R, true, true, 1.0, M, k, FIN_STEP);
+        std::swap(r0, r1);
+    }
+    PBK_CUDA(cudaEventRecord(ev3, stream));
+    PBK_CUDA(cudaEventSynchronize(ev3));
+    float ms = 0;
+    PBK_CUDA(cudaEventElapsedTime(&ms, ev2, ev3));
+    stats.step_ms += ms;
+}
+
+void Engine::run_offdiagonal(DeviceHamiltonian const& h, int M, bool opt_size, std::function<void(int, void*, double)> const& collect) {
+    void* r0 = vec_a.as();
+    void* r1 = vec_b.as();
+    PBK_CUDA(cudaEventRecord(ev2, stream));
+    int64_t init_rows = n;
+    if (opt_size) {
+        PBK_CUDA(cudaMemsetAsync(r1, 0, static_cast<size_t>(n) * dtype_size(dtype), stream));
+        init_rows = h.map.data[std::min(h.map.last_index(), h.map.src_offset + 1)];
+    }
+    step(h, r0, r1, nullptr, init_rows, 1, false, false, 0.5, M, 0, FIN_NONE);
+    collect(0, r0, 0.5);
+    collect(1, r1, 1.0);
+    for (int k = 2; k < M; ++k) {  // calc_moments::basic (off-diagonal), calc_moments.hpp:103-114
+        int64_t const rows = opt_size ? h.map.optimal_size(k, M) : n;
+        step(h, r1, r0, nullptr, rows, 1, true, false, 1.0, M, k, FIN_NONE);
+        std::swap(r0, r1);
+        collect(k, r1, 1.0);
+    }
+    PBK_CUDA(cudaEventRecord(ev3, stream));
+    PBK_CUDA(cudaEventSynchronize(ev3));
+    float ms = 0;
+    PBK_CUDA(cudaEventElapsedTime(&ms, ev2, ev3));
+    stats.step_ms += ms;
+}
+
+void Engine::reset_stats(int M, DeviceHamiltonian const& h, bool opt_size, double multiplier) {  // Stats.cpp:31-47
+    int64_t const h2d = stats.h2d_bytes;
+    stats = pbk_stats{};
+    stats.h2d_bytes = h2d;
+    stats.num_moments = M;
+    stats.uses_full_system = h.map.uses_full_system(M);
+    auto count = [&](bool opt, uint64_t per_row) {
+        uint64_t result = 0;
+        if (!opt) result = static_cast<uint64_t>(M) * n * per_row;
+        else for (int k = 0; k < M; ++k) result += static_cast<uint64_t>(h.map.optimal_size(k, M)) * per_row;
+        if (h.idx.is_diagonal()) result /= 2;
+        return result;
+    };
+    stats.nnz = count(false, h.ell.k);
+    stats.opt_nnz = count(opt_size, h.ell.k);
+    stats.vec = count(false, 1);
+    stats.opt_vec = count(opt_size, 1);
+    stats.multiplier = multiplier;
+    stats.matrix_memory = static_cast<uint64_t>(n) * h.ell.k * (dtype_size(dtype) + 4);
+    stats.vector_memory = static_cast<uint64_t>(n) * dtype_size(dtype);
+    stats.hamiltonian_time = h.seconds;
+    launches = 0;
+}
+
+void Engine::begin_moments() {
+    PBK_CUDA(cudaSetDevice(device));
+    moments_wall0 = now_seconds();
+}
+
+void Engine::end_moments() {
+    PBK_CUDA(cudaStreamSynchronize(stream));
+    stats.moments_time += now_seconds() - moments_wall0;
+    stats.kernel_launches = launches;
+    stats.eps = stats.moments_time > 0 ? stats.multiplier * static_cast<double>(stats.opt_nnz) / stats.moments_time : 0;
+}
+
+void Engine::shard(int total, int* first, int* count) const {
+    // contiguous blocks, remainder to the lowest ranks
+    int const base = total / world, rem = total % world;
+    *count = base + (rank < rem ? 1 : 0);
+    *first = rank * base + std::min(rank, rem);
+}
+
+void Engine::seed_stream(int64_t skip_vectors) {
+    PBK_CUDA(launch_mt_seed(mt_state.as<uint32_t>(), stream));
+    ++launches;
+    if (skip_vectors > 0) {
+        PBK_CUDA(launch_mt_generate(mt_state.as<uint32_t>(), nullptr, skip_vectors * n * dtype_words(dtype), stream));
+        ++launches;
+    }
+}
+
+void Engine::generate_random_block(DeviceHamiltonian const& h, int lanes, int R, void* dst) {
+    int64_t const words = static_cast<int64_t>(lanes) * n * dtype_words(dtype);
+    raw.ensure(sizeof(uint32_t) * words);
+    PBK_CUDA(cudaEventRecord(ev0, stream));
+    PBK_CUDA(launch_mt_generate(mt_state.as<uint32_t>(), raw.as<uint32_t>(), words, stream));
+    PBK_CUDA(launch_random_transform(dtype, raw.as<uint32_t>(), n, R, lanes, h.reordered ? h.perm.as<int32_t>() : nullptr, dst, stream));
+    PBK_CUDA(cudaEventRecord(ev1, stream));
+    launches += 2;
+    PBK_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0;
+    PBK_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    stats.starter_ms += ms;
+}
+
+void Engine::allreduce(double* dev, int64_t count) {
+    if (world <= 1 || !comm) return;
+    nccl->check(nccl->AllReduce(dev, dev, static_cast<size_t>(count), /*ncclDouble*/ 8, /*ncclSum*/ 0, comm, stream), "ncclAllReduce");
+}
+
+void Engine::comm_init(int world_, int rank_, const char* id) {
+    PBK_CUDA(cudaSetDevice(device));
+    comm_destroy();
+    if (world_ <= 1) { world = 1; rank = 0; return; }
+    if (!nccl) nccl = std::make_unique<NcclApi>();
+    NcclId uid;
+    std::memcpy(uid.bytes, id, sizeof(uid.bytes));
+    using InitFn = int (*)(void**, int, NcclId, int);
+    nccl->check(reinterpret_cast<InitFn>(nccl->init_rank)(&comm, world_, uid, rank_), "ncclCommInitRank");
+    world = world_;
+    rank = rank_;
+}
+
+void Engine::comm_destroy() {
+    if (comm && nccl) { nccl->CommDestroy(comm); }
+    comm = nullptr;
+    world = 1;
+    rank = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute-strategy level entry points
+// ------------------------------------------------------------------------------------------------
+static void check_num_moments(int M) {
+    if (M < 2 || M % 2 != 0) throw Error(PBK_INVALID_ARGUMENT, "pbkpm: num_moments must be an even number >= 2 (the reference uses 4k+2)");
+}
+
+void Engine::moments_dos(int M, int num_random, cd* out) {
+    check_num_moments(M);
+    if (num_random < 1) throw Error(PBK_INVALID_ARGUMENT, "num_random must be positive");
+    auto& h = natural_hamiltonian();
+    h.idx = Indices{{0}, {0}};
+    reset_stats(M, h, false, num_random);
+    int first = 0, count = 0;
+    shard(num_random, &first, &count);
+    begin_moments();
+    progress(-1, num_random);
+    ensure_moment_buffers(1, M);
+    PBK_CUDA(cudaMemsetAsync(acc.as(), 0, sizeof(double) * 2 * M, stream));
+    if (count > 0) {
+        int const rb = pick_batch(count, 0);
+        ensure_moment_buffers(rb, M);
+        size_t const block_bytes = static_cast<size_t>(n) * rb * dtype_size(dtype);
+        vec_a.ensure(block_bytes);
+        vec_b.ensure(block_bytes);
+        stats.batch = rb;
+        seed_stream(first);
+        for (int b0 = 0; b0 < count; b0 += rb) {
+            int const lanes = std::min(rb, count - b0);
+            int const R = lane_pad(lanes);
+            generate_random_block(h, lanes, R, vec_a.as());
+            run_diagonal(h, R, M, false);
+            PBK_CUDA(launch_accumulate_lanes(mom.as<double>(), lanes, M, acc.as<double>(), stream));
+            ++launches;
+            ++stats.num_batches;
+            progress(lanes, num_random);
+        }
+    }
+    allreduce(acc.as<double>(), 2 * M);
+    PBK_CUDA(cudaMemcpyAsync(out, acc.as(), sizeof(double) * 2 * M, cudaMemcpyDeviceToHost, stream));
+    stats.d2h_bytes += sizeof(double) * 2 * M;
+    end_moments();
+    if (num_random != 1) for (int i = 0; i < M; ++i) out[i] /= static_cast<double>(num_random);  // Moments.cpp:23-27
+    progress(num_random, num_random);
+}
+
+void Engine::moments_diagonal(int M, const cd* r0, int count, cd* out) {
+    check_num_moments(M);
+    auto& h = natural_hamiltonian();
+    reset_stats(M, h, false, count);
+    begin_moments();
+    int const rb = pick_batch(count, 0);
+    ensure_moment_buffers(rb, M);
+    size_t const block_bytes = static_cast<size_t>(n) * rb * dtype_size(dtype);
+    vec_a.ensure(block_bytes);
+    vec_b.ensure(block_bytes);
+    DevBuf staging(sizeof(double) * 2 * n);
+    std::vector<cd> host(static_cast<size_t>(rb) * M);
+    stats.batch = rb;
+    for (int b0 = 0; b0 < count; b0 += rb) {
+        int const lanes = std::min(rb, count - b0);
+        int const R = lane_pad(lanes);
+        PBK_CUDA(cudaMemsetAsync(vec_a.as(), 0, static_cast<size_t>(n) * R * dtype_size(dtype), stream));
+        for (int j = 0; j < lanes; ++j) {
+            PBK_CUDA(cudaMemcpyAsync(staging.as(), r0 + static_cast<size_t>(b0 + j) * n, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, stream));
+            PBK_CUDA(launch_scatter_block(dtype, staging.as<double>(), n, R, j, nullptr, vec_a.as(), stream));
+            PBK_CUDA(cudaStreamSynchronize(stream));
+            stats.h2d_bytes += sizeof(double) * 2 * n;
+        }
+        run_diagonal(h, R, M, false);
+        PBK_CUDA(cudaMemcpyAsync(host.data(), mom.as(), sizeof(cd) * static_cast<size_t>(lanes) * M, cudaMemcpyDeviceToHost, stream));
+        PBK_CUDA(cudaStreamSynchronize(stream));
+        for (int j = 0; j < lanes; ++j) for (int k = 0; k < M; ++k) out[static_cast<size_t>(k) * count + b0 + j] = host[static_cast<size_t>(j) * M + k];
+        ++stats.num_batches;
+    }
+    end_moments();
+}
+
+void Engine::random_vectors(int count, cd* out) {
+    auto& h = natural_hamiltonian();
+    PBK_CUDA(cudaSetDevice(device));
+    size_t const block_bytes = static_cast<size_t>(n) * dtype_size(dtype);
+    vec_a.ensure(block_bytes);
+    DevBuf staging(sizeof(double) * 2 * n);
+    seed_stream(0);
+    for (int j = 0; j < count; ++j) {
+        generate_random_block(h, 1, 1, vec_a.as());
+        PBK_CUDA(launch_extract_lane(dtype, vec_a.as(), n, 1, 0, staging.as<double>(), stream));
+        PBK_CUDA(cudaMemcpyAsync(out + static_cast<size_t>(j) * n, staging.as(), sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, stream));
+        PBK_CUDA(cudaStreamSynchronize(stream));
+    }
+}
+
+void Engine::moments_ldos(int M, const int32_t* idx, int nidx, cd* out) {
+    check_num_moments(M);
+    if (nidx < 1) throw Error(PBK_INVALID_ARGUMENT, "at least one index is required");
+    for (int i = 0; i < nidx; ++i) if (idx[i] < 0 || idx[i] >= n) throw Error(PBK_INVALID_ARGUMENT, "LDOS index out of range");
+    Indices target{std::vector<int32_t>(idx, idx + nidx), std::vector<int32_t>(idx, idx + nidx)};
+    auto& h = optimized_for(target);
+    bool const opt = config.optimal_size != 0 && h.reordered;
+    reset_stats(M, h, opt, nidx);
+    begin_moments();
+    progress(-1, nidx);
+    // sources are sharded over ranks in contiguous blocks; every rank returns the full table after the allreduce
+    int first = 0, count = 0;
+    shard(nidx, &first, &count);
+    std::vector<cd> table(static_cast<size_t>(M) * nidx, cd(0, 0));
+    if (count > 0) {
+        int const rb = pick_batch(count, 0);
+        ensure_moment_buffers(rb, M);
+        size_t const block_bytes = static_cast<size_t>(n) * rb * dtype_size(dtype);
+        vec_a.ensure(block_bytes);
+        vec_b.ensure(block_bytes);
+        idx_buf.ensure(sizeof(int32_t) * rb);
+        std::vector<cd> host(static_cast<size_t>(rb) * M);
+        stats.batch = rb;
+        for (int b0 = 0; b0 < count; b0 += rb) {
+            int const lanes = std::min(rb, count - b0);
+            int const R = lane_pad(lanes);
+            PBK_CUDA(cudaMemcpyAsync(idx_buf.as(), h.idx.src.data() + first + b0, sizeof(int32_t) * lanes, cudaMemcpyHostToDevice, stream));
+            PBK_CUDA(launch_unit_starter(dtype, vec_a.as(), n, R, idx_buf.as<int32_t>(), lanes, stream));
+            launches += 1;
+            run_diagonal(h, R, M, opt);
+            PBK_CUDA(cudaMemcpyAsync(host.data(), mom.as(), sizeof(cd) * static_cast<size_t>(lanes) * M, cudaMemcpyDeviceToHost, stream));
+            PBK_CUDA(cudaStreamSynchronize(stream));
+            stats.d2h_bytes += sizeof(cd) * static_cast<size_t>(lanes) * M;
+            for (int j = 0; j < lanes; ++j) for (int k = 0; k < M; ++k) table[static_cast<size_t>(k) * nidx + first + b0 + j] = host[static_cast<size_t>(j) * M + k];
+            ++stats.num_batches;
+            progress(lanes, nidx);
+        }
+    }
+    if (world > 1) {
+        DevBuf t(sizeof(cd) * table.size());
+        PBK_CUDA(cudaMemcpyAsync(t.as(), table.data(), sizeof(cd) * table.size(), cudaMemcpyHostToDevice, stream));
+        allreduce(t.as<double>(), static_cast<int64_t>(2 * table.size()));
+        PBK_CUDA(cudaMemcpyAsync(table.data(), t.as(), sizeof(cd) * table.size(), cudaMemcpyDeviceToHost, stream));
+        PBK_CUDA(cudaStreamSynchronize(stream));
+    }
+    std::copy(table.begin(), table.end(), out);
+    end_moments();
+    progress(nidx, nidx);
+}
+
+void Engine::moments_greens(int M, int row, const int32_t* cols, int ncols, cd* out) {
+    check_num_moments(M);
+    if (ncols < 1) throw Error(PBK_INVALID_ARGUMENT, "at least one column index is required");
+    Indices target{{row}, std::vector<int32_t>(cols, cols + ncols)};
+    auto& h = optimized_for(target);
+    bool const opt = config.optimal_size != 0 && h.reordered;
+    reset_stats(M, h, opt, 1);
+    begin_moments();
+    size_t const vbytes = static_cast<size_t>(n) * lane_pad(1) * dtype_size(dtype);
+    vec_a.ensure(vbytes);
+    vec_b.ensure(vbytes);
+    stats.batch = 1;
+    stats.num_batches = 1;
+    idx_buf.ensure(sizeof(int32_t) * std::max(ncols, 1));
+    if (h.idx.is_diagonal()) {  // Core.cpp:106-110
+        ensure_moment_buffers(lane_pad(1), M);
+        int const R = lane_pad(1);
+        PBK_CUDA(cudaMemcpyAsync(idx_buf.as(), h.idx.src.data(), sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+        PBK_CUDA(launch_unit_starter(dtype, vec_a.as(), n, R, idx_buf.as<int32_t>(), 1, stream));
+        ++launches;
+        run_diagonal(h, R, M, opt);
+        PBK_CUDA(cudaMemcpyAsync(out, mom.as(), sizeof(cd) * M, cudaMemcpyDeviceToHost, stream));
+    } else {                    // Core.cpp:111-115, MultiUnitCollector
+        ensure_moment_buffers(std::max(ncols, 1), M);
+        PBK_CUDA(cudaMemcpyAsync(idx_buf.as(), h.idx.src.data(), sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+        PBK_CUDA(launch_unit_starter(dtype, vec_a.as(), n, 1, idx_buf.as<int32_t>(), 1, stream));
+        PBK_CUDA(cudaMemcpyAsync(idx_buf.as(), h.idx.dest.data(), sizeof(int32_t) * ncols, cudaMemcpyHostToDevice, stream));
+        ++launches;
+        run_offdiagonal(h, M, opt, [&](int k, void* r, double scale) {
+            PBK_CUDA(launch_gather_moment(dtype, r, 1, idx_buf.as<int32_t>(), ncols, mom.as<double>(), M, k, scale, stream));
+            ++launches;
+        });
+        PBK_CUDA(cudaMemcpyAsync(out, mom.as(), sizeof(cd) * static_cast<size_t>(ncols) * M, cudaMemcpyDeviceToHost, stream));
+    }
+    stats.d2h_bytes += sizeof(cd) * static_cast<size_t>(ncols) * M;
+    end_moments();
+}
+
+void Engine::moments_kubo(int M, const float* left, const float* right, int num_random, cd* out) {
+    check_num_moments(M);
+    if (num_random < 1) throw Error(PBK_INVALID_ARGUMENT, "num_random must be positive");
+    auto& h = natural_hamiltonian();
+    reset_stats(M, h, false, num_random);
+    DeviceHamiltonian vl, vr;
+    upload_operator(vl, left);
+    upload_operator(vr, right);
+    int const s = dtype_size(dtype);
+    size_t const vbytes = static_cast<size_t>(n) * s;
+    size_t const stack_bytes = vbytes * M;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (2.0 * stack_bytes + 4.0 * vbytes > 0.9 * static_cast<double>(free_b)) {
+        throw Error(PBK_RUNTIME_ERROR, "pbkpm: the two num_moments x system_size Kubo-Bastin stacks do not fit in device memory");
+    }
+    begin_moments();
+    progress(-1, num_random);
+    DevBuf lstack(stack_bytes), rstack(stack_bytes), u(vbytes), mu(sizeof(cd) * static_cast<size_t>(M) * M);
+    vec_a.ensure(vbytes);
+    vec_b.ensure(vbytes);
+    ensure_moment_buffers(1, M);
+    PBK_CUDA(cudaMemsetAsync(mu.as(), 0, mu.bytes(), stream));
+    int first = 0, count = 0;
+    shard(num_random, &first, &count);
+    seed_stream(first);
+    stats.batch = 1;
+    auto row_of = [&](DevBuf& st, int k) { return static_cast<void*>(st.as<char>() + static_cast<size_t>(k) * vbytes); };
+    for (int j = 0; j < count; ++j) {
+        generate_random_block(h, 1, 1, u.as());
+        PBK_CUDA(cudaEventRecord(ev2, stream));
+        // left: starter v_l|r>, rows are T_n(H) v_l |r>            (Core.cpp:131-133, DenseMatrixCollector)
+        void* r0 = vec_a.as(); void* r1 = vec_b.as();
+        step(vl, u.as(), r0, nullptr, n, 1, false, false, 1.0, M, 0, FIN_NONE);
+        step(vl, u.as(), row_of(lstack, 0), nullptr, n, 1, false, false, 0.5, M, 0, FIN_NONE);
+        step(h, r0, r1, row_of(lstack, 1), n, 1, false, false, 0.5, M, 0, FIN_NONE);
+        for (int k = 2; k < M; ++k) { step(h, r1, r0, row_of(lstack, k), n, 1, true, false, 1.0, M, k, FIN_NONE); std::swap(r0, r1); }
+        // right: starter |r>, rows are v_r T_n(H)|r>                 (Core.cpp:135-137)
+        r0 = u.as(); r1 = vec_b.as();
+        step(vr, r0, row_of(rstack, 0), nullptr, n, 1, false, false, 0.5, M, 0, FIN_NONE);
+        step(h, r0, r1, nullptr, n, 1, false, false, 0.5, M, 0, FIN_NONE);
+        step(vr, r1, row_of(rstack, 1), nullptr, n, 1, false, false, 1.0, M, 0, FIN_NONE);
+        // r0 (= u) is overwritten from here on; its content is no longer needed
+        for (int k = 2; k < M; ++k) {
+            step(h, r1, r0, nullptr, n, 1, true, false, 1.0, M, k, FIN_NONE);
+            std::swap(r0, r1);
+            step(vr, r1, row_of(rstack, k), nullptr, n, 1, false, false, 1.0, M, k, FIN_NONE);
+        }
+        PBK_CUDA(cudaEventRecord(ev3, stream));
+        double flops = 0;
+        PBK_CUDA(launch_kubo_gemm(dtype, lstack.as(), rstack.as(), M, n, mu.as<double>(), num_sms, stream, &flops));
+        launches += dtype_complex(dtype) ? 4 : 2;
+        PBK_CUDA(cudaEventRecord(ev1, stream));
+        PBK_CUDA(cudaEventSynchronize(ev1));
+        float ms = 0;
+        PBK_CUDA(cudaEventElapsedTime(&ms, ev2, ev3));
+        stats.step_ms += ms;
+        PBK_CUDA(cudaEventElapsedTime(&ms, ev3, ev1));
+        stats.gemm_ms += ms;
+        stats.gemm_flops += flops;
+        ++stats.num_batches;
+        progress(1, num_random);
+    }
+    allreduce(mu.as<double>(), 2LL * M * M);
+    PBK_CUDA(cudaMemcpyAsync(out, mu.as(), mu.bytes(), cudaMemcpyDeviceToHost, stream));
+    stats.d2h_bytes += static_cast<int64_t>(mu.bytes());
+    end_moments();
+    for (size_t i = 0; i < static_cast<size_t>(M) * M; ++i) out[i] /= static_cast<double>(num_random);  // Moments.cpp:127-130
+    progress(num_random, num_random);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kpm::Core level
+// ------------------------------------------------------------------------------------------------
+void Engine::core_moments(int num_moments, const cd* alpha, const cd* beta, int64_t op_rows, const int32_t* op_indptr,
+                          const int32_t* op_indices, const cd* op_data, cd* out) {
+    if (num_moments < 1) throw Error(PBK_INVALID_ARGUMENT, "num_moments must be positive");
+    int const M = round_num_moments(num_moments);
+    auto& h = natural_hamiltonian();
+    std::vector<cd> m(M);
+    if (!beta && op_rows == 0) {  // Core.cpp:45-49
+        moments_diagonal(M, alpha, 1, m.data());
+    } else {                      // Core.cpp:50-55, GenericCollector
+        reset_stats(M, h, false, 1);
+        DeviceHamiltonian op;
+        if (op_rows != 0) upload_csr_operator(op, op_rows, op_indptr, op_indices, op_data);
+        begin_moments();
+        size_t const vbytes = static_cast<size_t>(n) * dtype_size(dtype);
+        vec_a.ensure(vbytes);
+        vec_b.ensure(vbytes);
+        vec_t.ensure(vbytes);
+        ensure_moment_buffers(1, M);
+        DevBuf staging(sizeof(double) * 2 * n), beta_dev(vbytes);
+        PBK_CUDA(cudaMemcpyAsync(staging.as(), beta ? beta : alpha, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, stream));
+        PBK_CUDA(launch_scatter_block(dtype, staging.as<double>(), n, 1, 0, nullptr, beta_dev.as(), stream));
+        PBK_CUDA(cudaStreamSynchronize(stream));
+        PBK_CUDA(cudaMemcpyAsync(staging.as(), alpha, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, stream));
+        PBK_CUDA(launch_scatter_block(dtype, staging.as<double>(), n, 1, 0, nullptr, vec_a.as(), stream));
+        stats.h2d_bytes += 2 * sizeof(double) * 2 * n;
+        run_offdiagonal(h, M, false, [&](int k, void* r, double scale) {
+            const void* v = r;
+            if (op.valid) {
+                step(op, r, vec_t.as(), nullptr, n, 1, false, false, 1.0, M, k, FIN_NONE);
+                v = vec_t.as();
+            }
+            PBK_CUDA(launch_dot_moment(dtype, beta_dev.as(), v, n, mom.as<double>(), k, scale, scratch.as<double>(), counter.as<unsigned>(), num_sms, stream));
+            ++launches;
+        });
+        PBK_CUDA(cudaMemcpyAsync(m.data(), mom.as(), sizeof(cd) * M, cudaMemcpyDeviceToHost, stream));
+        end_moments();
+    }
+    auto const g = damping_coefficients(config.kernel, config.lambda_value, M);
+    for (int i = 0; i < num_moments; ++i) out[i] = m[i] * g[i];
+}
+
+void Engine::calc_dos(const double* energy, int ne, double broadening, int num_random, double* out) {
+    double const t0 = now_seconds();
+    auto const s = scaling_factors();
+    int const M = required_num_moments(broadening);
+    std::vector<cd> m(M);
+    moments_dos(M, num_random, m.data());
+    auto const g = damping_coefficients(config.kernel, config.lambda_value, M);
+    for (int i = 0; i < M; ++i) m[i] *= g[i];
+    reconstruct_spectral_density(m.data(), M, 1, 0, 1, energy, ne, s, out);
+    last_total_seconds = now_seconds() - t0;
+}
+
+void Engine::calc_ldos(const double* energy, int ne, double broadening, const int32_t* idx, int nidx, double* out) {
+    double const t0 = now_seconds();
+    auto const s = scaling_factors();
+    int const M = required_num_moments(broadening);
+    std::vector<cd> m(static_cast<size_t>(M) * nidx);
+    moments_ldos(M, idx, nidx, m.data());
+    auto const g = damping_coefficients(config.kernel, config.lambda_value, M);
+    for (int k = 0; k < M; ++k) for (int i = 0; i < nidx; ++i) m[static_cast<size_t>(k) * nidx + i] *= g[k];
+    reconstruct_spectral_density(m.data(), M, nidx, 1, nidx, energy, ne, s, out);
+    last_total_seconds = now_seconds() - t0;
+}
+
+void Engine::calc_greens(int row, const int32_t* cols, int ncols, const double* energy, int ne, double broadening, cd* out) {
+    double const t0 = now_seconds();
+    auto const s = scaling_factors();
+    int const M = required_num_moments(broadening);
+    std::vector<cd> m(static_cast<size_t>(M) * ncols);
+    moments_greens(M, row, cols, ncols, m.data());
+    auto const g = damping_coefficients(config.kernel, config.lambda_value, M);
+    for (int i = 0; i < ncols; ++i) {
+        for (int k = 0; k < M; ++k) m[static_cast<size_t>(i) * M + k] *= g[k];
+        reconstruct_greens(m.data() + static_cast<size_t>(i) * M, M, energy, ne, s, out + static_cast<size_t>(i) * ne);
+    }
+    last_total_seconds = now_seconds() - t0;
+}
+
+void Engine::calc_conductivity(const float* left, const float* right, const double* mu, int nmu, double broadening,
+                               double temperature, int num_random, int num_points, cd* out) {
+    double const t0 = now_seconds();
+    auto const s = scaling_factors();
+    int const M = required_num_moments(broadening);
+    std::vector<cd> m(static_cast<size_t>(M) * M);
+    moments_kubo(M, left, right, num_random, m.data());
+    auto const g = damping_coefficients(config.kernel, config.lambda_value, M);
+    for (int i = 0; i < M; ++i) for (int j = 0; j < M; ++j) m[static_cast<size_t>(i) * M + j] *= g[i] * g[j];  // Kernel.hpp:49-56
+
+    // energy samples: linspace over the *unscaled* bounds (Bounds.hpp:54), then scaled
+    std::vector<double> samples(num_points);
+    for (int i = 0; i < num_points; ++i) {
+        double const e = (i == num_points - 1) ? bounds_max : bounds_min + i * ((bounds_max - bounds_min) / std::max(1, num_points - 1));
+        samples[i] = (e - s.b) / s.a;
+    }
+    // sum_nm(E) = 1/(1-E^2)^2 * sum_{m,n} mu_mn * Gamma_mn(E): O(points * M^2) -> on the device
+    DevBuf mu_dev(sizeof(cd) * m.size()), samples_dev(sizeof(double) * num_points), sum_dev(sizeof(cd) * num_points);
+    PBK_CUDA(cudaMemcpyAsync(mu_dev.as(), m.data(), sizeof(cd) * m.size(), cudaMemcpyHostToDevice, stream));
+    PBK_CUDA(cudaMemcpyAsync(samples_dev.as(), samples.data(), sizeof(double) * num_points, cudaMemcpyHostToDevice, stream));
+    PBK_CUDA(launch_kubo_gamma_sum(mu_dev.as<double>(), M, samples_dev.as<double>(), num_points, sum_dev.as<double>(), stream));
+    std::vector<double> sum_nm(2 * static_cast<size_t>(num_points));
+    PBK_CUDA(cudaMemcpyAsync(sum_nm.data(), sum_dev.as(), sizeof(cd) * num_points, cudaMemcpyDeviceToHost, stream));
+    PBK_CUDA(cudaStreamSynchronize(stream));
+    reconstruct_kubo_bastin(sum_nm.data(), samples, mu, nmu, temperature, s, out);
+    last_total_seconds = now_seconds() - t0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reporting (Core::report, Bounds::report, Stats::report)
+// ------------------------------------------------------------------------------------------------
+static std::string with_suffix(double v) {
+    char const* suffix[] = {"", "k", "M", "G", "T", "P"};
+    int i = 0;
+    while (std::abs(v) >= 1000 && i < 5) { v /= 1000; ++i; }
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), (i == 0 || v >= 100) ? "%.0f%s" : (v >= 10 ? "%.1f%s" : "%.2f%s"), v, suffix[i]);
+    return buf;
+}
+static std::string duration(double s) {
+    char buf[64];
+    if (s < 1e-3) std::snprintf(buf, sizeof(buf), "%.0fus", s * 1e6);
+    else if (s < 1) std::snprintf(buf, sizeof(buf), "%.2fms", s * 1e3);
+    else std::snprintf(buf, sizeof(buf), "%.2fs", s);
+    return buf;
+}
+
+std::string Engine::report(bool shortform) const {
+    char buf[1024];
+    double const removed = stats.nnz > 0 ? 100.0 * static_cast<double>(stats.nnz - stats.opt_nnz) / static_cast<double>(stats.nnz) : 0.0;
+    char const* star = stats.uses_full_system ? "" : "*";
+    if (shortform) {
+        std::snprintf(buf, sizeof(buf), "%.2f, %.2f, %d [%s] %.0f%%%s [%s] %s @ %seps [%s] | %s", bounds_min, bounds_max, lanczos_loops,
+                      duration(bounds_seconds).c_str(), removed, star, duration(stats.hamiltonian_time).c_str(),
+                      with_suffix(static_cast<double>(stats.num_moments)).c_str(), with_suffix(stats.eps).c_str(),
+                      duration(stats.moments_time).c_str(), duration(last_total_seconds).c_str());
+    } else {
+        std::snprintf(buf, sizeof(buf),
+                      "- Spectrum bounds found (%.2f, %.2f eV) using Lanczos procedure with %d loops | %s\n"
+                      "- The reordering optimization was able to remove %.0f%%%s of the workload | %s\n"
+                      "- KPM calculated %s moments at %s non-zero elements per second (B200, %d vectors/pass) | %s\n"
+                      "Total time: %s",
+                      bounds_min, bounds_max, lanczos_loops, duration(bounds_seconds).c_str(), removed, star,
+                      duration(stats.hamiltonian_time).c_str(), with_suffix(static_cast<double>(stats.num_moments)).c_str(),
+                      with_suffix(stats.eps).c_str(), stats.batch, duration(stats.moments_time).c_str(),
+                      duration(last_total_seconds).c_str());
+    }
+    return buf;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reconstruction (kpm/reconstruct.hpp), double precision; the reference's float constants are kept
+// ------------------------------------------------------------------------------------------------
+void reconstruct_spectral_density(const cd* moments, int M, int cols, int64_t col_stride, int64_t n_stride,
+                                  const double* energy, int ne, Scale s, double* out) {
+    double const k = static_cast<double>(2 / pi_f) / s.a;  // real_t{2 / constant::pi}
+    for (int c = 0; c < cols; ++c) {
+        for (int i = 0; i < ne; ++i) {
+            double const E = (energy[i] - s.b) / s.a;
+            double const ac = std::acos(E);
+            double sum = 0;
+            for (int q = 0; q < M; ++q) sum += moments[q * n_stride + c * col_stride].real() * std::cos(q * ac);
+            out[static_cast<size_t>(c) * ne + i] = k / std::sqrt(1 - E * E) * sum;
+        }
+    }
+}
+
+void reconstruct_greens(const cd* moments, int M, const double* energy, int ne, Scale s, cd* out) {
+    cd const i1(0, 1);
+    cd const k = -2.0 * i1 / s.a;
+    for (int i = 0; i < ne; ++i) {
+        double const E = (energy[i] - s.b) / s.a;
+        double const ac = std::acos(E);
+        cd sum(0, 0);
+        for (int q = 0; q < M; ++q) sum += moments[q] * std::exp(-i1 * (q * ac));
+        out[i] = k / std::sqrt(1 - E * E) * sum;
+    }
+}
+
+void reconstruct_kubo_bastin(const double* sum_nm, const std::vector<double>& en, const double* mu, int nmu,
+                             double temperature, Scale s, cd* out) {
+    int const np = static_cast<int>(en.size());
+    double const inv_kbt_sc = s.a / (kb_f * temperature);
+    double const en_max = *std::max_element(en.begin(), en.end());
+    double const en_min = *std::min_element(en.begin(), en.end());
+    double const coeff = (en_max - en_min) / static_cast<double>(2 * np);
+    cd const prefix = cd(4.0) / (s.a * s.a);
+    for (int j = 0; j < nmu; ++j) {
+        double const mi = (mu[j] - s.b) / s.a;
+        cd total(0, 0), first(0, 0), last(0, 0);
+        for (int p = 0; p < np; ++p) {
+            double const fd = 1.0 / (1.0 + std::exp((en[p] - mi) * inv_kbt_sc));
+            cd const f = fd * cd(sum_nm[2 * p], sum_nm[2 * p + 1]);
+            total += f;
+            if (p == 0) first = f;
+            if (p == np - 1) last = f;
+        }
+        out[j] = prefix * (coeff * (2.0 * total - first - last));
+    }
+}
+
+} // namespace pbk

@@ -1,0 +1,238 @@
+// engine.hpp -- host side of libpbkpm.so: the B200 counterpart of kpm::Core + DefaultCompute.
+#pragma once
+#include "../../include/pbkpm.h"
+#include "kernels.cuh"
+
+#include <complex>
+#include <dlfcn.h>
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace pbk {
+
+using cd = std::complex<double>;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int code, std::string const& msg) : std::runtime_error(msg), code(code) {}
+};
+
+void cuda_check(cudaError_t err, char const* what, char const* file, int line);
+#define PBK_CUDA(call) ::pbk::cuda_check((call), #call, __FILE__, __LINE__)
+
+/// RAII device allocation
+class DevBuf {
+public:
+    DevBuf() = default;
+    explicit DevBuf(size_t bytes) { alloc(bytes); }
+    DevBuf(DevBuf const&) = delete;
+    DevBuf& operator=(DevBuf const&) = delete;
+    DevBuf(DevBuf&& o) noexcept : ptr(o.ptr), size(o.size) { o.ptr = nullptr; o.size = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); ptr = o.ptr; size = o.size; o.ptr = nullptr; o.size = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void alloc(size_t bytes);
+    void ensure(size_t bytes) { if (bytes > size) { release(); alloc(bytes); } }
+    void release();
+    template<class T = void> T* as() const { return static_cast<T*>(ptr); }
+    size_t bytes() const { return size; }
+private:
+    void* ptr = nullptr;
+    size_t size = 0;
+};
+
+/// kpm::Scale (cppcore/include/kpm/Bounds.hpp:11-33) including its single-precision constants
+struct Scale {
+    double a = 0, b = 0;
+    Scale() = default;
+    Scale(double min_energy, double max_energy);
+};
+
+/// kpm::SliceMap (cppcore/include/kpm/OptimizedHamiltonian.hpp:54-96)
+struct SliceMap {
+    std::vector<int32_t> data;
+    int src_offset = 0, dest_offset = 0;
+    int last_index() const { return static_cast<int>(data.size()) - 1; }
+    int index(int n, int num_moments) const;
+    int64_t optimal_size(int n, int num_moments) const { return data[index(n, num_moments)]; }
+    bool uses_full_system(int num_moments) const { return static_cast<int>(data.size()) < num_moments / 2; }
+};
+
+struct Indices {
+    std::vector<int32_t> src, dest;
+    bool is_diagonal() const { return src == dest; }
+    bool operator==(Indices const& o) const { return src == o.src && dest == o.dest; }
+};
+
+/// Device-resident scaled (and optionally BFS-reordered) Hamiltonian in slot-major ELL
+struct DeviceHamiltonian {
+    bool valid = false;
+    bool reordered = false;
+    Indices original_idx, idx;     // idx: positions in the device ordering
+    SliceMap map;
+    std::vector<int32_t> reorder_map;  // original -> device row (empty: identity)
+    DevBuf val, col, perm;
+    EllDev ell;
+    double seconds = 0;
+    uint64_t memory() const { return static_cast<uint64_t>(ell.rows) * ell.k * 0 + val.bytes() + col.bytes(); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen: no link-time dependency, single-GPU use never touches it
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+
+    NcclApi() {
+        for (char const* name : {"libnccl.so.2", "libnccl.so"}) {
+            handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) throw Error(PBK_NCCL_ERROR, std::string("cannot load libnccl.so.2: ") + dlerror());
+        GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(handle, "ncclGetUniqueId"));
+        AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(handle, "ncclAllReduce"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
+        init_rank = dlsym(handle, "ncclCommInitRank");
+        if (!GetUniqueId || !AllReduce || !CommDestroy || !init_rank) throw Error(PBK_NCCL_ERROR, "libnccl is missing required symbols");
+    }
+    void* init_rank = nullptr;
+    void check(int r, char const* what) const {
+        if (r != 0) throw Error(PBK_NCCL_ERROR, std::string("NCCL error in ") + what + ": " + (GetErrorString ? GetErrorString(r) : "?"));
+    }
+};
+struct NcclId { char bytes[128]; };  // ncclUniqueId
+
+
+class Engine {
+public:
+    Engine(int device, pbk_config const& config);
+    ~Engine();
+
+    std::mutex mutex;            // one in-flight calculation per context
+    std::string last_error;
+
+    void set_progress(pbk_progress_fn fn, void* user) { progress_fn = fn; progress_user = user; }
+    void set_hamiltonian(int dtype, int64_t n, const int32_t* indptr, const int32_t* indices, const void* data);
+
+    void bounds(double* mn, double* mx, int32_t* loops);
+    Scale scaling_factors();
+    int required_num_moments(double broadening);
+
+    // compute-strategy level
+    void moments_dos(int M, int num_random, cd* out);
+    void moments_ldos(int M, const int32_t* idx, int nidx, cd* out);
+    void moments_greens(int M, int row, const int32_t* cols, int ncols, cd* out);
+    void moments_kubo(int M, const float* left, const float* right, int num_random, cd* out);
+    void moments_diagonal(int M, const cd* r0, int count, cd* out);
+    void random_vectors(int count, cd* out);
+
+    // kpm::Core level
+    void core_moments(int num_moments, const cd* alpha, const cd* beta, int64_t op_rows, const int32_t* op_indptr,
+                      const int32_t* op_indices, const cd* op_data, cd* out);
+    void calc_dos(const double* energy, int ne, double broadening, int num_random, double* out);
+    void calc_ldos(const double* energy, int ne, double broadening, const int32_t* idx, int nidx, double* out);
+    void calc_greens(int row, const int32_t* cols, int ncols, const double* energy, int ne, double broadening, cd* out);
+    void calc_conductivity(const float* left, const float* right, const double* mu, int nmu, double broadening,
+                           double temperature, int num_random, int num_points, cd* out);
+
+    pbk_stats get_stats() const { return stats; }
+    std::string report(bool shortform) const;
+
+    void comm_init(int world, int rank, const char* id);
+    void comm_destroy();
+
+private:
+    // ---- configuration / device ----
+    int device = 0;
+    int num_sms = 148;
+    pbk_config config{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    pbk_progress_fn progress_fn = nullptr;
+    void* progress_user = nullptr;
+
+    // ---- host copy of the Hamiltonian (original order, unscaled) ----
+    int dtype = -1;
+    int64_t n = 0;
+    std::vector<int32_t> h_indptr, h_indices;
+    std::vector<char> h_data;
+    bool has_h = false;
+
+    // ---- bounds ----
+    bool have_bounds = false;
+    double bounds_min = 0, bounds_max = 0;
+    int lanczos_loops = 0;
+    double bounds_seconds = 0;
+
+    // ---- device Hamiltonians ----
+    DeviceHamiltonian natural;    // scaled, original order (DOS / conductivity / moments)
+    DeviceHamiltonian optimized;  // scaled + BFS-reordered for the last (src, dest) request (LDOS / Green's)
+    DeviceHamiltonian unscaled;   // original values, original order (Lanczos)
+
+    // ---- work buffers ----
+    DevBuf vec_a, vec_b, vec_t, raw, mom, m01, acc, partials, counter, scratch, mt_state, idx_buf;
+
+    // ---- multi-GPU ----
+    std::unique_ptr<NcclApi> nccl;
+    void* comm = nullptr;
+    int world = 1, rank = 0;
+
+    pbk_stats stats{};
+    double last_total_seconds = 0;
+
+    // ---- helpers ----
+    void require_hamiltonian() const;
+    void compute_bounds();
+    void build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, bool reorder, Indices const& target);
+    DeviceHamiltonian& natural_hamiltonian();
+    DeviceHamiltonian& optimized_for(Indices const& target);
+    DeviceHamiltonian& unscaled_hamiltonian();
+    void upload_operator(DeviceHamiltonian& dh, const float* positions);  // velocity operator (natural order)
+    void upload_csr_operator(DeviceHamiltonian& dh, int64_t rows, const int32_t* indptr, const int32_t* indices, const cd* data);
+
+    int pick_batch(int vectors, int extra_blocks) const;
+    int lane_pad(int R) const;
+    void ensure_moment_buffers(int R, int M);
+    void step(DeviceHamiltonian const& h, const void* x, void* y, void* y2, int64_t nrows, int R, bool subtract, bool sums,
+              double scale, int M, int nstep, int fin);
+    /// diagonal recursion for the R vectors in vec_a (r0); moments land in `mom` ([R][M] c128)
+    void run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_size);
+    /// off-diagonal recursion for the single vector in vec_a; `collect(n, r, half)` is called for every moment
+    void run_offdiagonal(DeviceHamiltonian const& h, int M, bool opt_size, std::function<void(int, void*, double)> const& collect);
+    void reset_stats(int M, DeviceHamiltonian const& h, bool opt_size, double multiplier);
+    void begin_moments();
+    void end_moments();
+    void progress(int64_t delta, int64_t total) { if (progress_fn) progress_fn(delta, total, progress_user); }
+    void generate_random_block(DeviceHamiltonian const& h, int lanes, int R, void* dst);
+    void seed_stream(int64_t skip_vectors);
+
+    void shard(int total, int* first, int* count) const;
+    void allreduce(double* dev, int64_t count);
+
+    double moments_wall0 = 0;
+    int64_t launches = 0;
+};
+
+// kernels (src/kpm/Kernel.cpp:6-49)
+int round_num_moments(int n);
+std::vector<double> damping_coefficients(int kernel, double lambda_value, int n);
+int kernel_required_num_moments(int kernel, double lambda_value, double scaled_broadening);
+
+// reconstruction (include/kpm/reconstruct.hpp:16-143), double precision with the reference's float constants
+void reconstruct_spectral_density(const cd* moments, int M, int cols, int64_t col_stride, int64_t n_stride,
+                                  const double* energy, int ne, Scale s, double* out);
+void reconstruct_greens(const cd* moments, int M, const double* energy, int ne, Scale s, cd* out);
+void reconstruct_kubo_bastin(const double* sum_nm_c128, const std::vector<double>& scaled_samples, const double* mu, int nmu,
+                             double temperature, Scale s, cd* out);
+cudaError_t launch_kubo_gamma_sum(const double* mu_c128, int M, const double* scaled_samples, int np, double* out_c128, cudaStream_t s);
+
+} // namespace pbk

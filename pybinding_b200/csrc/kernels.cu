@@ -1,0 +1,553 @@
+// kernels.cu -- hand-written sm_100a kernels of the KPM hot path.
+//
+// K1/K2/K3 `cheb_step`: one fused Chebyshev step for a block of R vectors,
+//     y[row, :] = sum_s val[s][row] * x[col[s][row], :]  -  y[row, :]          (rows < nrows)
+// optionally fused with the two per-vector reductions of the diagonal algorithm
+//     m2[r] = sum_row |x[row, r]|^2 ,   m3[r] = sum_row conj(y_new[row, r]) * x[row, r]
+// and with the moment bookkeeping (the last block to finish reduces the per-block partial sums in
+// a fixed order and writes mu_{2(n-1)} = 2 (m2 - m0), mu_{2n-1} = 2 m3 - m1 straight into the device
+// moment array), so one launch per step is all a diagonal KPM run needs.
+//
+// Replaces, from the reference (cppcore/): compute::kpm_spmv / kpm_spmv_diagonal
+// (include/compute/kernel_polynomial.hpp:19-326), make_r1 (include/kpm/Starter.hpp:55-118), the
+// Diagonal/BatchDiagonal collectors (src/kpm/default/collectors.cpp:6-34) and the thread-pool
+// batching of DefaultCompute (src/kpm/default/Compute.cpp:52-88).
+//
+// Layout: H in slot-major ELL (val[s * pitch + row], col[s * pitch + row]); vectors as an N x R
+// row-major block so one matrix element feeds R contiguous lanes.  Each thread owns one 16-byte
+// chunk (V lanes) of one row: a warp touches 512 contiguous bytes of y / x[row] and gathers whole
+// 16-byte chunks of x[col] -- every access is a full-sector vector load.  The (col, val) pair of a
+// thread's *next* row is prefetched while the gathers of the current row are in flight, which
+// removes the index -> gather dependency from the critical path.  Dot products are accumulated in
+// double regardless of the vector type.
+#include "kernels.cuh"
+
+#include <cstdio>
+
+namespace pbk {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// scalar helpers
+// ------------------------------------------------------------------------------------------------
+template<class T> struct ST;
+template<> struct ST<float>   { using real = float;  static constexpr bool cplx = false; static constexpr int C = 2; };
+template<> struct ST<double>  { using real = double; static constexpr bool cplx = false; static constexpr int C = 2; };
+template<> struct ST<float2>  { using real = float;  static constexpr bool cplx = true;  static constexpr int C = 3; };
+template<> struct ST<double2> { using real = double; static constexpr bool cplx = true;  static constexpr int C = 3; };
+
+__device__ __forceinline__ float zero_(float) { return 0.f; }
+__device__ __forceinline__ double zero_(double) { return 0.0; }
+__device__ __forceinline__ float2 zero_(float2) { return make_float2(0.f, 0.f); }
+__device__ __forceinline__ double2 zero_(double2) { return make_double2(0.0, 0.0); }
+
+__device__ __forceinline__ float neg_(float a) { return -a; }
+__device__ __forceinline__ double neg_(double a) { return -a; }
+__device__ __forceinline__ float2 neg_(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ double2 neg_(double2 a) { return make_double2(-a.x, -a.y); }
+
+// acc + a * x  (complex: 4 FMAs, same association as compute::detail::mul + add)
+__device__ __forceinline__ float fma_(float a, float x, float acc) { return fmaf(a, x, acc); }
+__device__ __forceinline__ double fma_(double a, double x, double acc) { return fma(a, x, acc); }
+__device__ __forceinline__ float2 fma_(float2 a, float2 x, float2 acc) {
+    acc.x = fmaf(a.x, x.x, acc.x); acc.x = fmaf(-a.y, x.y, acc.x);
+    acc.y = fmaf(a.x, x.y, acc.y); acc.y = fmaf(a.y, x.x, acc.y);
+    return acc;
+}
+__device__ __forceinline__ double2 fma_(double2 a, double2 x, double2 acc) {
+    acc.x = fma(a.x, x.x, acc.x); acc.x = fma(-a.y, x.y, acc.x);
+    acc.y = fma(a.x, x.y, acc.y); acc.y = fma(a.y, x.x, acc.y);
+    return acc;
+}
+__device__ __forceinline__ float scale_(float a, double s) { return a * static_cast<float>(s); }
+__device__ __forceinline__ double scale_(double a, double s) { return a * s; }
+__device__ __forceinline__ float2 scale_(float2 a, double s) { float f = static_cast<float>(s); return make_float2(a.x * f, a.y * f); }
+__device__ __forceinline__ double2 scale_(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
+
+// acc[0] += |x|^2 ; acc[1] (+ acc[2]) += conj(y) * x   -- in double
+__device__ __forceinline__ void sums_(double* acc, float x, float y) {
+    double const xd = x, yd = y; acc[0] = fma(xd, xd, acc[0]); acc[1] = fma(yd, xd, acc[1]);
+}
+__device__ __forceinline__ void sums_(double* acc, double x, double y) { acc[0] = fma(x, x, acc[0]); acc[1] = fma(y, x, acc[1]); }
+__device__ __forceinline__ void sums_(double* acc, float2 x, float2 y) {
+    double const xr = x.x, xi = x.y, yr = y.x, yi = y.y;
+    acc[0] = fma(xr, xr, acc[0]); acc[0] = fma(xi, xi, acc[0]);
+    acc[1] = fma(yr, xr, acc[1]); acc[1] = fma(yi, xi, acc[1]);
+    acc[2] = fma(yr, xi, acc[2]); acc[2] = fma(-yi, xr, acc[2]);
+}
+__device__ __forceinline__ void sums_(double* acc, double2 x, double2 y) {
+    acc[0] = fma(x.x, x.x, acc[0]); acc[0] = fma(x.y, x.y, acc[0]);
+    acc[1] = fma(y.x, x.x, acc[1]); acc[1] = fma(y.y, x.y, acc[1]);
+    acc[2] = fma(y.x, x.y, acc[2]); acc[2] = fma(-y.y, x.x, acc[2]);
+}
+
+/// V elements of T moved as one vector access (16 bytes when V * sizeof(T) == 16)
+template<class T, int V> struct alignas(V * sizeof(T)) Chunk { T e[V]; };
+
+template<class CH> __device__ __forceinline__ CH load_nc(const CH* p) {  // read-only path (ld.global.nc)
+    CH r;
+    if constexpr (sizeof(CH) == 16) { int4 t = __ldg(reinterpret_cast<const int4*>(p)); r = *reinterpret_cast<CH*>(&t); }
+    else if constexpr (sizeof(CH) == 8) { int2 t = __ldg(reinterpret_cast<const int2*>(p)); r = *reinterpret_cast<CH*>(&t); }
+    else { int t = __ldg(reinterpret_cast<const int*>(p)); r = *reinterpret_cast<CH*>(&t); }
+    return r;
+}
+template<class CH> __device__ __forceinline__ CH load_cs(const CH* p) {  // streaming: read once
+    CH r;
+    if constexpr (sizeof(CH) == 16) { int4 t = __ldcs(reinterpret_cast<const int4*>(p)); r = *reinterpret_cast<CH*>(&t); }
+    else if constexpr (sizeof(CH) == 8) { int2 t = __ldcs(reinterpret_cast<const int2*>(p)); r = *reinterpret_cast<CH*>(&t); }
+    else { int t = __ldcs(reinterpret_cast<const int*>(p)); r = *reinterpret_cast<CH*>(&t); }
+    return r;
+}
+template<class CH> __device__ __forceinline__ void store_(CH* p, CH const& v) {
+    if constexpr (sizeof(CH) == 16) { *reinterpret_cast<int4*>(p) = *reinterpret_cast<const int4*>(&v); }
+    else if constexpr (sizeof(CH) == 8) { *reinterpret_cast<int2*>(p) = *reinterpret_cast<const int2*>(&v); }
+    else { *reinterpret_cast<int*>(p) = *reinterpret_cast<const int*>(&v); }
+}
+template<class T> __device__ __forceinline__ T ldg_scalar(const T* p) {
+    Chunk<T, 1> c = load_nc(reinterpret_cast<const Chunk<T, 1>*>(p));
+    return c.e[0];
+}
+
+constexpr int MAX_TPB = 256;
+
+struct StepDev {  // POD copy of StepArgs for the kernel
+    const void* val; const int32_t* col; int64_t pitch; int k;
+    const void* x; void* y; void* y2;
+    int64_t nrows; int R; int cpr; int rpb;
+    double scale;
+    double* partials; unsigned* counter; double* mom; double* m01; int M; int n; int fin;
+};
+
+// ------------------------------------------------------------------------------------------------
+// The fused step kernel.  K > 0: ELL width known at compile time (unrolled + prefetched); K == 0: generic.
+// ------------------------------------------------------------------------------------------------
+template<class T, int V, int K, bool SUB, bool SUMS>
+__global__ void __launch_bounds__(MAX_TPB) cheb_step(StepDev a) {
+    using CH = Chunk<T, V>;
+    constexpr int C = ST<T>::C;
+    constexpr int NACC = V * C;
+    constexpr int KK = K > 0 ? K : 1;
+
+    const T* __restrict__ val = static_cast<const T*>(a.val);
+    const int32_t* __restrict__ col = a.col;
+    const CH* __restrict__ x = static_cast<const CH*>(a.x);
+    CH* __restrict__ y = static_cast<CH*>(a.y);
+    CH* __restrict__ y2 = static_cast<CH*>(a.y2);
+
+    int const cpr = a.cpr;                       // 16-byte chunks per row
+    int const tx = threadIdx.x % cpr;            // chunk within the row
+    int const ty = threadIdx.x / cpr;            // row within the block
+    int64_t const stride = static_cast<int64_t>(gridDim.x) * a.rpb;
+    int64_t row = static_cast<int64_t>(blockIdx.x) * a.rpb + ty;
+
+    double acc[NACC];
+#pragma unroll
+    for (int q = 0; q < NACC; ++q) acc[q] = 0.0;
+
+    if constexpr (K > 0) {
+        int32_t c[KK]; T v[KK];
+        if (row < a.nrows) {
+#pragma unroll
+            for (int s = 0; s < KK; ++s) { c[s] = __ldg(col + s * a.pitch + row); v[s] = ldg_scalar(val + s * a.pitch + row); }
+        }
+        while (row < a.nrows) {
+            int64_t const next = row + stride;
+            // gathers of the current row (independent loads, all in flight together)
+            CH xg[KK];
+#pragma unroll
+            for (int s = 0; s < KK; ++s) xg[s] = load_nc(x + static_cast<int64_t>(c[s]) * cpr + tx);
+            CH yv, xr;
+            if constexpr (SUB) yv = load_cs(y + row * cpr + tx);
+            if constexpr (SUMS) xr = load_nc(x + row * cpr + tx);
+            // prefetch the next row's matrix entries while the gathers fly
+            int32_t cn[KK]; T vn[KK];
+            if (next < a.nrows) {
+#pragma unroll
+                for (int s = 0; s < KK; ++s) { cn[s] = __ldg(col + s * a.pitch + next); vn[s] = ldg_scalar(val + s * a.pitch + next); }
+            }
+            CH out;
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                T r = SUB ? neg_(yv.e[e]) : zero_(T{});
+#pragma unroll
+                for (int s = 0; s < KK; ++s) r = fma_(v[s], xg[s].e[e], r);
+                if constexpr (!SUB) r = scale_(r, a.scale);
+                out.e[e] = r;
+                if constexpr (SUMS) sums_(acc + e * C, xr.e[e], r);
+            }
+            store_(y + row * cpr + tx, out);
+            if (y2) store_(y2 + row * cpr + tx, out);
+#pragma unroll
+            for (int s = 0; s < KK; ++s) { c[s] = cn[s]; v[s] = vn[s]; }
+            row = next;
+        }
+    } else {
+        for (; row < a.nrows; row += stride) {
+            CH out;
+#pragma unroll
+            for (int e = 0; e < V; ++e) out.e[e] = zero_(T{});
+            if constexpr (SUB) {
+                CH yv = load_cs(y + row * cpr + tx);
+#pragma unroll
+                for (int e = 0; e < V; ++e) out.e[e] = neg_(yv.e[e]);
+            }
+            for (int s = 0; s < a.k; ++s) {
+                int32_t const cc = __ldg(col + s * a.pitch + row);
+                T const vv = ldg_scalar(val + s * a.pitch + row);
+                CH const xg = load_nc(x + static_cast<int64_t>(cc) * cpr + tx);
+#pragma unroll
+                for (int e = 0; e < V; ++e) out.e[e] = fma_(vv, xg.e[e], out.e[e]);
+            }
+            if constexpr (!SUB) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) out.e[e] = scale_(out.e[e], a.scale);
+            }
+            if constexpr (SUMS) {
+                CH const xr = load_nc(x + row * cpr + tx);
+#pragma unroll
+                for (int e = 0; e < V; ++e) sums_(acc + e * C, xr.e[e], out.e[e]);
+            }
+            store_(y + row * cpr + tx, out);
+            if (y2) store_(y2 + row * cpr + tx, out);
+        }
+    }
+
+    if constexpr (SUMS) {
+        // ---- block reduction over the rows of the block (tree over ty, fixed order) ----
+        __shared__ double sm[MAX_TPB * NACC];
+        __shared__ bool is_last;
+        int const tid = threadIdx.x;
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) sm[tid * NACC + q] = acc[q];
+        int p2 = 1;
+        while (p2 < a.rpb) p2 <<= 1;
+        for (int s = p2 >> 1; s > 0; s >>= 1) {
+            __syncthreads();
+            if (ty < s && ty + s < a.rpb) {
+#pragma unroll
+                for (int q = 0; q < NACC; ++q) sm[tid * NACC + q] += sm[(tid + s * cpr) * NACC + q];
+            }
+        }
+        __syncthreads();
+        int const RC = a.R * C;
+        if (ty == 0) {
+#pragma unroll
+            for (int q = 0; q < NACC; ++q) a.partials[static_cast<int64_t>(blockIdx.x) * RC + tx * NACC + q] = sm[tx * NACC + q];
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) { is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1); }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+
+        // ---- last block: reduce over blocks in a fixed order and write the moments ----
+        int const nt = blockDim.x;
+        int const nb = gridDim.x;
+        auto finalize = [&](int o, double s) {
+            int const lane = o / C, comp = o % C;
+            if (a.fin == FIN_INIT) {
+                if (comp == 0) { double m0 = 0.5 * s; a.m01[lane * 3 + 0] = m0; a.mom[(static_cast<int64_t>(lane) * a.M + 0) * 2] = m0; a.mom[(static_cast<int64_t>(lane) * a.M + 0) * 2 + 1] = 0.0; }
+                else if (comp == 1) { a.m01[lane * 3 + 1] = s; a.mom[(static_cast<int64_t>(lane) * a.M + 1) * 2] = s; if (C == 2) { a.m01[lane * 3 + 2] = 0.0; a.mom[(static_cast<int64_t>(lane) * a.M + 1) * 2 + 1] = 0.0; } }
+                else { a.m01[lane * 3 + 2] = s; a.mom[(static_cast<int64_t>(lane) * a.M + 1) * 2 + 1] = s; }
+            } else if (a.fin == FIN_STEP) {
+                int64_t const i0 = static_cast<int64_t>(lane) * a.M + 2 * (a.n - 1);
+                if (comp == 0) { a.mom[i0 * 2] = 2.0 * (s - a.m01[lane * 3 + 0]); a.mom[i0 * 2 + 1] = 0.0; }
+                else if (comp == 1) { a.mom[(i0 + 1) * 2] = 2.0 * s - a.m01[lane * 3 + 1]; if (C == 2) a.mom[(i0 + 1) * 2 + 1] = 0.0; }
+                else { a.mom[(i0 + 1) * 2 + 1] = 2.0 * s - a.m01[lane * 3 + 2]; }
+            }
+        };
+        if (RC >= nt) {
+            for (int o = tid; o < RC; o += nt) {
+                double s = 0.0;
+                for (int b = 0; b < nb; ++b) s += a.partials[static_cast<int64_t>(b) * RC + o];
+                finalize(o, s);
+            }
+        } else {
+            int const G = nt / RC;
+            int const g = tid / RC, o = tid % RC;
+            double s = 0.0;
+            if (g < G) { for (int b = g; b < nb; b += G) s += a.partials[static_cast<int64_t>(b) * RC + o]; }
+            __syncthreads();
+            if (g < G) sm[g * RC + o] = s;
+            __syncthreads();
+            if (tid < RC) {
+                double t = 0.0;
+                for (int gg = 0; gg < G; ++gg) t += sm[gg * RC + tid];
+                finalize(tid, t);
+            }
+        }
+        if (tid == 0) *a.counter = 0u;
+    }
+}
+
+template<class T, int V, int K>
+cudaError_t launch_step_vk(StepDev const& d, bool sub, bool sums, int grid, int block, cudaStream_t stream) {
+    if (sub && sums) cheb_step<T, V, K, true, true><<<grid, block, 0, stream>>>(d);
+    else if (sub) cheb_step<T, V, K, true, false><<<grid, block, 0, stream>>>(d);
+    else if (sums) cheb_step<T, V, K, false, true><<<grid, block, 0, stream>>>(d);
+    else cheb_step<T, V, K, false, false><<<grid, block, 0, stream>>>(d);
+    return cudaGetLastError();
+}
+
+template<class T, int V>
+cudaError_t launch_step_v(StepDev const& d, bool sub, bool sums, int grid, int block, cudaStream_t stream, int* kused) {
+    switch (d.k) {
+        case 3: *kused = 3; return launch_step_vk<T, V, 3>(d, sub, sums, grid, block, stream);
+        case 4: *kused = 4; return launch_step_vk<T, V, 4>(d, sub, sums, grid, block, stream);
+        case 7: *kused = 7; return launch_step_vk<T, V, 7>(d, sub, sums, grid, block, stream);
+        default: *kused = 0; return launch_step_vk<T, V, 0>(d, sub, sums, grid, block, stream);
+    }
+}
+
+template<class T>
+cudaError_t launch_step_t(StepArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info) {
+    constexpr int VMAX = 16 / sizeof(T);
+    int V = VMAX;
+    while (V > 1 && a.R % V != 0) V >>= 1;
+    if (VMAX == 4 && V == 2) V = 1;  // only the full-width and the scalar variants are instantiated
+    int const cpr = a.R / V;
+    if (cpr > MAX_TPB) return cudaErrorInvalidValue;
+    int const rpb = MAX_TPB / cpr;
+    int const block = rpb * cpr;
+    int64_t const need = (a.nrows + rpb - 1) / rpb;
+    int grid = static_cast<int>(need < static_cast<int64_t>(max_step_blocks(num_sms)) ? need : max_step_blocks(num_sms));
+    if (grid < 1) grid = 1;
+
+    StepDev d{a.h.val, a.h.col, a.h.pitch, a.h.k, a.x, a.y, a.y2, a.nrows, a.R, cpr, rpb, a.scale,
+              a.partials, a.counter, a.mom, a.m01, a.M, a.n, a.fin};
+    int kused = 0;
+    cudaError_t err;
+    if (V == VMAX && VMAX > 1) err = launch_step_v<T, VMAX>(d, a.subtract, a.sums, grid, block, stream, &kused);
+    else err = launch_step_v<T, 1>(d, a.subtract, a.sums, grid, block, stream, &kused);
+    if (info) { info->grid = grid; info->block = block; info->V = V; info->K = kused; }
+    return err;
+}
+
+} // anonymous namespace
+
+int max_step_blocks(int num_sms) { return num_sms * 8; }
+
+cudaError_t launch_step(int dtype, StepArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info) {
+    if (a.nrows <= 0) return cudaSuccess;
+    switch (dtype) {
+        case F32: return launch_step_t<float>(a, num_sms, stream, info);
+        case C64: return launch_step_t<float2>(a, num_sms, stream, info);
+        case F64: return launch_step_t<double>(a, num_sms, stream, info);
+        case C128: return launch_step_t<double2>(a, num_sms, stream, info);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ================================================================================================
+// small helper kernels
+// ================================================================================================
+namespace {
+
+template<class T> __device__ __forceinline__ T from_c128(double re, double im);
+template<> __device__ __forceinline__ float from_c128<float>(double re, double) { return static_cast<float>(re); }
+template<> __device__ __forceinline__ double from_c128<double>(double re, double) { return re; }
+template<> __device__ __forceinline__ float2 from_c128<float2>(double re, double im) { return make_float2(static_cast<float>(re), static_cast<float>(im)); }
+template<> __device__ __forceinline__ double2 from_c128<double2>(double re, double im) { return make_double2(re, im); }
+__device__ __forceinline__ double re_(float a) { return a; }
+__device__ __forceinline__ double re_(double a) { return a; }
+__device__ __forceinline__ double re_(float2 a) { return a.x; }
+__device__ __forceinline__ double re_(double2 a) { return a.x; }
+__device__ __forceinline__ double im_(float) { return 0.0; }
+__device__ __forceinline__ double im_(double) { return 0.0; }
+__device__ __forceinline__ double im_(float2 a) { return a.y; }
+__device__ __forceinline__ double im_(double2 a) { return a.y; }
+
+template<class T>
+__global__ void unit_starter_kernel(T* dst, int R, const int32_t* src, int nsrc) {
+    int const lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane < nsrc) dst[static_cast<int64_t>(src[lane]) * R + lane] = from_c128<T>(1.0, 0.0);
+}
+
+template<class T>
+__global__ void gather_moment_kernel(const T* v, int R, const int32_t* idx, int nidx, double* mom, int64_t M, int n, double scale) {
+    int const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nidx) return;
+    T const e = v[static_cast<int64_t>(idx[i]) * R];
+    mom[(static_cast<int64_t>(i) * M + n) * 2] = re_(e) * scale;
+    mom[(static_cast<int64_t>(i) * M + n) * 2 + 1] = im_(e) * scale;
+}
+
+/// Deterministic grid reduction of NV doubles per thread: block tree, then the last block sums the partials in order.
+template<int NV, class Fin>
+__device__ void grid_reduce(double (&v)[NV], double* scratch, unsigned* counter, Fin fin) {
+    __shared__ double sm[256 * NV];
+    __shared__ bool is_last;
+    int const tid = threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) sm[tid * NV + q] = v[q];
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        __syncthreads();
+        if (tid < s) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) sm[tid * NV + q] += sm[(tid + s) * NV + q];
+        }
+    }
+    __syncthreads();
+    if (tid < NV) scratch[static_cast<int64_t>(blockIdx.x) * NV + tid] = sm[tid];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double t[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) t[q] = 0.0;
+    for (int b = tid; b < static_cast<int>(gridDim.x); b += blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) t[q] += scratch[static_cast<int64_t>(b) * NV + q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NV; ++q) sm[tid * NV + q] = t[q];
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        __syncthreads();
+        if (tid < s) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) sm[tid * NV + q] += sm[(tid + s) * NV + q];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { fin(sm); *counter = 0u; }
+}
+
+template<class T>
+__global__ void __launch_bounds__(256) dot_moment_kernel(const T* beta, const T* v, int64_t n_rows, double* mom, int n, double scale,
+                                                         double* scratch, unsigned* counter) {
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_rows; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        double const br = re_(beta[i]), bi = im_(beta[i]), vr = re_(v[i]), vi = im_(v[i]);
+        acc[0] += br * vr + bi * vi;   // conj(beta) * v
+        acc[1] += br * vi - bi * vr;
+    }
+    grid_reduce<2>(acc, scratch, counter, [&](double* s) { mom[2 * n] = s[0] * scale; mom[2 * n + 1] = s[1] * scale; });
+}
+
+__global__ void accumulate_lanes_kernel(const double* mom, int R, int M, double* acc) {
+    int const i = blockIdx.x * blockDim.x + threadIdx.x;  // over 2*M doubles
+    if (i >= 2 * M) return;
+    double s = 0.0;
+    for (int lane = 0; lane < R; ++lane) s += mom[static_cast<int64_t>(lane) * M * 2 + i];
+    acc[i] += s;
+}
+
+template<class T>
+__global__ void scatter_block_kernel(const double* src, int64_t n, int R, int lane, const int32_t* perm, T* dst) {
+    int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t const row = perm ? perm[i] : i;
+    dst[row * R + lane] = from_c128<T>(src[2 * i], src[2 * i + 1]);
+}
+
+template<class T>
+__global__ void extract_lane_kernel(const T* v, int64_t n, int R, int lane, double* out) {
+    int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T const e = v[i * R + lane];
+    out[2 * i] = re_(e); out[2 * i + 1] = im_(e);
+}
+
+// ---- Lanczos -----------------------------------------------------------------------------------
+template<class T> __device__ __forceinline__ T axpy_(double a, T x, T y);  // y - a*x
+template<> __device__ __forceinline__ float axpy_(double a, float x, float y) { return y - static_cast<float>(a) * x; }
+template<> __device__ __forceinline__ double axpy_(double a, double x, double y) { return y - a * x; }
+template<> __device__ __forceinline__ float2 axpy_(double a, float2 x, float2 y) { float f = static_cast<float>(a); return make_float2(y.x - f * x.x, y.y - f * x.y); }
+template<> __device__ __forceinline__ double2 axpy_(double a, double2 x, double2 y) { return make_double2(y.x - a * x.x, y.y - a * x.y); }
+
+/// v0 = t - b_prev*v0 - a*v1 ; out = |v0|^2     (lanczos_spmv + lanczos_axpy of compute/lanczos.hpp:26-98)
+template<class T>
+__global__ void __launch_bounds__(256) lanczos_update_kernel(const T* t, const T* v1, T* v0, int64_t n, double b_prev, const double* a_dev,
+                                                             double* out, double* scratch, unsigned* counter) {
+    double const a = a_dev[0];
+    double acc[1] = {0.0};
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        T w = axpy_<T>(b_prev, v0[i], t[i]);
+        w = axpy_<T>(a, v1[i], w);
+        v0[i] = w;
+        acc[0] += re_(w) * re_(w) + im_(w) * im_(w);
+    }
+    grid_reduce<1>(acc, scratch, counter, [&](double* s) { out[0] = s[0]; });
+}
+
+template<class T>
+__global__ void scale_inv_sqrt_kernel(T* v, int64_t n, const double* norm2) {
+    double const f = 1.0 / sqrt(norm2[0]);
+    int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = scale_(v[i], f);
+}
+
+inline int blocks_for(int64_t n, int tpb, int cap) {
+    int64_t b = (n + tpb - 1) / tpb;
+    if (b < 1) b = 1;
+    return static_cast<int>(b < cap ? b : cap);
+}
+
+} // anonymous namespace
+
+#define PBK_DISPATCH(dtype, CALL)                                   \
+    switch (dtype) {                                                \
+        case F32: { using T = float; CALL; break; }                 \
+        case C64: { using T = float2; CALL; break; }                \
+        case F64: { using T = double; CALL; break; }                \
+        case C128: { using T = double2; CALL; break; }              \
+        default: return cudaErrorInvalidValue;                      \
+    }
+
+cudaError_t launch_unit_starter(int dtype, void* dst, int64_t n, int R, const int32_t* src_dev, int nsrc, cudaStream_t s) {
+    cudaError_t err = cudaMemsetAsync(dst, 0, static_cast<size_t>(n) * R * dtype_size(dtype), s);
+    if (err != cudaSuccess || nsrc == 0) return err;
+    PBK_DISPATCH(dtype, (unit_starter_kernel<T><<<(nsrc + 127) / 128, 128, 0, s>>>(static_cast<T*>(dst), R, src_dev, nsrc)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_moment(int dtype, const void* v, int R, const int32_t* idx_dev, int nidx, double* mom, int64_t M, int n,
+                                 double scale, cudaStream_t s) {
+    PBK_DISPATCH(dtype, (gather_moment_kernel<T><<<(nidx + 127) / 128, 128, 0, s>>>(static_cast<const T*>(v), R, idx_dev, nidx, mom, M, n, scale)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dot_moment(int dtype, const void* beta, const void* v, int64_t n_rows, double* mom, int n, double scale,
+                              double* scratch, unsigned* counter, int num_sms, cudaStream_t s) {
+    int const grid = blocks_for(n_rows, 256, num_sms * 4);
+    PBK_DISPATCH(dtype, (dot_moment_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(beta), static_cast<const T*>(v), n_rows, mom, n, scale, scratch, counter)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_accumulate_lanes(const double* mom, int R, int M, double* acc, cudaStream_t s) {
+    accumulate_lanes_kernel<<<(2 * M + 255) / 256, 256, 0, s>>>(mom, R, M, acc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_block(int dtype, const double* src_c128, int64_t n, int R, int lane, const int32_t* perm_dev, void* dst, cudaStream_t s) {
+    int const grid = static_cast<int>((n + 255) / 256);
+    PBK_DISPATCH(dtype, (scatter_block_kernel<T><<<grid, 256, 0, s>>>(src_c128, n, R, lane, perm_dev, static_cast<T*>(dst))));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_extract_lane(int dtype, const void* v, int64_t n, int R, int lane, double* out_c128, cudaStream_t s) {
+    int const grid = static_cast<int>((n + 255) / 256);
+    PBK_DISPATCH(dtype, (extract_lane_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(v), n, R, lane, out_c128)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lanczos_update(int dtype, int64_t n, const void* t, const void* v1, void* v0, double b_prev, const double* a_dev,
+                                  double* out, double* scratch, unsigned* counter, int num_sms, cudaStream_t s) {
+    int const grid = blocks_for(n, 256, num_sms * 4);
+    PBK_DISPATCH(dtype, (lanczos_update_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(t), static_cast<const T*>(v1), static_cast<T*>(v0), n, b_prev, a_dev, out, scratch, counter)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scale_inv_sqrt(int dtype, int64_t n, void* v, const double* norm2_dev, cudaStream_t s) {
+    int const grid = static_cast<int>((n + 255) / 256);
+    PBK_DISPATCH(dtype, (scale_inv_sqrt_kernel<T><<<grid, 256, 0, s>>>(static_cast<T*>(v), n, norm2_dev)));
+    return cudaGetLastError();
+}
+
+} // namespace pbk

@@ -1,0 +1,92 @@
+// kernels.cuh -- type-erased launch interface between the host engine and the sm_100a kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pbk {
+
+enum DType : int { F32 = 0, C64 = 1, F64 = 2, C128 = 3 };
+inline int dtype_size(int dt) { return dt == F32 ? 4 : (dt == C128 ? 16 : 8); }
+inline bool dtype_complex(int dt) { return dt == C64 || dt == C128; }
+inline int dtype_words(int dt) { return (dt == F32 || dt == C64) ? 1 : 2; }  // MT19937 words per draw
+
+/// Device ELL matrix, slot-major: element (row, s) at s * pitch + row
+struct EllDev {
+    void* val = nullptr;     // scalar type of the Hamiltonian
+    int32_t* col = nullptr;
+    int64_t rows = 0;
+    int64_t pitch = 0;
+    int k = 0;
+};
+
+/// What the last block of a fused step kernel does with the reduced sums
+enum FinMode : int { FIN_NONE = 0, FIN_INIT = 1, FIN_STEP = 2 };
+
+struct StepArgs {
+    EllDev h;
+    const void* x = nullptr;   // N x R row-major block (gathered operand)
+    void* y = nullptr;         // N x R block: read (SUB) and written
+    void* y2 = nullptr;        // optional second destination, same layout as y
+    int64_t nrows = 0;         // rows [0, nrows) are processed
+    int R = 1;                 // vectors advanced together
+    bool subtract = true;      // y = H*x - y   (else y = scale * H*x)
+    bool sums = false;         // fused sum|x|^2 and sum conj(y_new)*x per vector
+    double scale = 1.0;
+    // fused moment bookkeeping (sums only)
+    double* partials = nullptr;  // [grid][R*C]
+    unsigned* counter = nullptr;
+    double* mom = nullptr;       // c128 [R][M]
+    double* m01 = nullptr;       // [R][3]: m0, re(m1), im(m1)
+    int M = 0;
+    int n = 0;                   // FIN_STEP: writes moments 2(n-1) and 2(n-1)+1
+    int fin = FIN_NONE;
+};
+
+struct LaunchInfo { int grid = 0, block = 0, V = 0, K = 0; };
+
+/// Fused Chebyshev step (K1/K2/K3).  Returns the launch geometry used (for stats / tests).
+cudaError_t launch_step(int dtype, StepArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info);
+/// Upper bound of blocks launch_step may use (size of the partials buffer = this * R * 3 doubles)
+int max_step_blocks(int num_sms);
+
+// ---- small helpers -------------------------------------------------------------------------------
+/// dst[i * R + lane] = (i == src[lane]) for lane < nsrc, 0 elsewhere (UnitStarter); dst is zero-filled first
+cudaError_t launch_unit_starter(int dtype, void* dst, int64_t n, int R, const int32_t* src_dev, int nsrc, cudaStream_t s);
+/// out[i * stride_out + n] = v[idx[i] * R + lane0]  (MultiUnitCollector); mom is c128
+cudaError_t launch_gather_moment(int dtype, const void* v, int R, const int32_t* idx_dev, int nidx, double* mom,
+                                 int64_t M, int n, double scale, cudaStream_t s);
+/// mom[n] = scale * sum_i conj(beta[i]) * v[i]   (GenericCollector), deterministic two-pass
+cudaError_t launch_dot_moment(int dtype, const void* beta, const void* v, int64_t n_rows, double* mom, int n, double scale,
+                              double* scratch, unsigned* counter, int num_sms, cudaStream_t s);
+/// acc[n] += sum_{lane < R} mom[lane][n]  (BatchAccumulator)
+cudaError_t launch_accumulate_lanes(const double* mom, int R, int M, double* acc, cudaStream_t s);
+/// dst[perm ? perm[i] : i][lane] = cast(src c128 [i]) -- ConstantStarter upload (src on device, c128)
+cudaError_t launch_scatter_block(int dtype, const double* src_c128, int64_t n, int R, int lane, const int32_t* perm_dev,
+                                 void* dst, cudaStream_t s);
+/// out c128[i] = v[i * R + lane]
+cudaError_t launch_extract_lane(int dtype, const void* v, int64_t n, int R, int lane, double* out_c128, cudaStream_t s);
+
+// ---- random starters (mt19937.cu) ------------------------------------------------------------
+constexpr int MT_N = 624;
+/// state_dev: 624 words + 1 position word.  Seeds std::mt19937's default state (seed 5489, position 624).
+cudaError_t launch_mt_seed(uint32_t* state_dev, cudaStream_t s);
+/// Write the next `count` tempered outputs of the stream to `out` (out == nullptr: just skip them)
+cudaError_t launch_mt_generate(uint32_t* state_dev, uint32_t* out, int64_t count, cudaStream_t s);
+/// raw words [lanes_filled][n*w] -> N x R block of +-1 (real) or exp(i*2*pi_f*u) (complex), RandomStarter;
+/// lanes >= lanes_filled are zeroed.  perm_dev (optional): destination row of site i (reorder map).
+cudaError_t launch_random_transform(int dtype, const uint32_t* raw, int64_t n, int R, int lanes_filled, const int32_t* perm_dev,
+                                    void* dst, cudaStream_t s);
+
+// ---- Kubo-Bastin contraction (kubo.cu) -------------------------------------------------------
+/// C (M x M, c128 row-major) += A (M x N) * B^H (N x M); A, B row-major stacks of the Hamiltonian's scalar type
+cudaError_t launch_kubo_gemm(int dtype, const void* A, const void* B, int M, int64_t N, double* C_c128, int num_sms,
+                             cudaStream_t s, double* flops);
+
+// ---- Lanczos helpers (bounds) ----------------------------------------------------------------
+/// v0 = t - b_prev*v0 - a*v1 (a read from a_dev[0]) ; out[0] = |v0|^2
+cudaError_t launch_lanczos_update(int dtype, int64_t n, const void* t, const void* v1, void* v0, double b_prev, const double* a_dev,
+                                  double* out, double* scratch, unsigned* counter, int num_sms, cudaStream_t s);
+/// v *= 1/sqrt(norm2[0])
+cudaError_t launch_scale_inv_sqrt(int dtype, int64_t n, void* v, const double* norm2_dev, cudaStream_t s);
+
+} // namespace pbk
