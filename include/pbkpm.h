@@ -66,6 +66,9 @@ typedef struct pbk_config {
     int32_t matrix_format;   /* 0 = CSR, 1 = ELL; accepted for API compatibility, the device layout is always ELL */
     float lanczos_precision; /* percent, default 0.002 */
     int32_t max_batch;       /* max. KPM vectors advanced together in one pass over H (0 = automatic) */
+    int32_t locality_tile;   /* full-system runs (DOS, conductivity, moments): sites are relabelled into breadth-first
+                                clusters of this many rows so that gathers stay on-chip; 0 = automatic, < 0 = keep
+                                the caller's site order.  Results do not depend on it beyond summation rounding. */
 } pbk_config;
 
 /* kpm::Stats (cppcore/include/kpm/Stats.hpp:19-45, cppmodule/src/kpm.cpp:50-66) + GPU counters. */
@@ -172,6 +175,15 @@ int pbk_calc_greens(pbk_ctx* ctx, int32_t row, const int32_t* cols, int32_t ncol
 int pbk_calc_conductivity(pbk_ctx* ctx, const float* left, const float* right,
                           const double* chemical_potential, int32_t num_mu, double broadening,
                           double temperature, int32_t num_random, int32_t num_points, void* out);
+
+/* The relabelling used for full-system runs (see pbk_config.locality_tile): order[new_row] = original row.
+ * Host-only helper (no device needed); exposed so that callers / tests can inspect the layout. */
+int pbk_locality_order(int64_t n, const int32_t* indptr, const int32_t* indices, int32_t tile, int32_t* order);
+
+/* Host-only check of the MT19937 jump-ahead used for segment-parallel starter generation: writes the 624-word
+ * generator window positioned so that window[1..623] are the raw (untempered) words of draws
+ * [position, position + 623) of a default-seeded std::mt19937. */
+int pbk_mt_jump_window(uint64_t position, uint32_t* window);
 
 /* ---- reporting ------------------------------------------------------------------------------ */
 /* replaces: Core::get_stats / KPMStats (cppmodule/src/kpm.cpp:50-66) */

@@ -1014,7 +1014,7 @@ struct CoreBase {
     virtual void calc_greens(int row, std::vector<int> const& cols, double const* e, int ne, double broadening, cd* out) = 0;
     virtual void calc_conductivity(float const* left, float const* right, double const* mu, int nmu, double broadening,
                                    double temperature, int num_random, int num_points, cd* out) = 0;
-    virtual double time_dos_steps(int num_moments, int num_random, int num_threads) = 0;
+    virtual double time_dos_steps(int num_moments, int num_random, int num_threads, bool cheap_starter) = 0;
 };
 
 template<class T, bool HP> struct Core : CoreBase {
@@ -1355,12 +1355,26 @@ template<class T, bool HP> struct Core : CoreBase {
     }
 
     /// CPU baseline: time the reference-shaped DOS moment computation (threads over SIMD batches)
-    double time_dos_steps(int num_moments, int num_random, int num_threads) override {
+    double time_dos_steps(int num_moments, int num_random, int num_threads, bool cheap_starter) override {
         optimize_for({{0}, {0}});
         auto const saved = config.num_threads;
         config.num_threads = num_threads;
         moments_seconds = 0;
         auto starter = random_starter();
+        if (cheap_starter) {
+            // Timing aid for bounded CPU samples: unit-modulus +-1 entries from a xorshift generator instead of
+            // the reference's mutex-serialised MT19937 (+ complex exp) starter, whose fixed cost per vector would
+            // dominate a run with few moments.  The recursion cost does not depend on the values.
+            auto state = std::make_shared<uint64_t>(0x9E3779B97F4A7C15ull);
+            int const size = oh.size();
+            starter.make = [state, size]() {
+                std::vector<T> r0(size);
+                uint64_t x = *state;
+                for (auto& v : r0) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; v = (x & 1u) ? T(1) : T(-1); }
+                *state = x;
+                return r0;
+            };
+        }
         (void)batch_diagonal(num_moments, num_random, starter, false, true);
         config.num_threads = saved;
         return moments_seconds;
@@ -1476,8 +1490,8 @@ int orc_calc_conductivity(void* p, float const* left, float const* right, double
 
 int orc_last_num_moments(void* p) { return static_cast<CoreBase*>(p)->last_num_moments; }
 double orc_moments_seconds(void* p) { return static_cast<CoreBase*>(p)->moments_seconds; }
-int orc_time_dos(void* p, int M, int num_random, int num_threads, double* seconds) { ORC_TRY
-    *seconds = static_cast<CoreBase*>(p)->time_dos_steps(M, num_random, num_threads); ORC_CATCH }
+int orc_time_dos(void* p, int M, int num_random, int num_threads, int cheap_starter, double* seconds) { ORC_TRY
+    *seconds = static_cast<CoreBase*>(p)->time_dos_steps(M, num_random, num_threads, cheap_starter != 0); ORC_CATCH }
 int orc_hardware_threads() { return static_cast<int>(std::thread::hardware_concurrency()); }
 
 } // extern "C"

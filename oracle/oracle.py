@@ -240,8 +240,11 @@ class OracleKPM:
     def moments_seconds(self):
         return lib().orc_moments_seconds(self.handle)
 
-    def time_dos(self, num_moments, num_random, num_threads):
-        """Seconds spent in the reference-shaped DOS moment computation (cpu_baseline)"""
+    def time_dos(self, num_moments, num_random, num_threads, cheap_starter=False):
+        """Seconds spent in the reference-shaped DOS moment computation (cpu_baseline).
+
+        cheap_starter=True replaces the reference's serial MT19937 (+ complex exp) starter by a trivial +-1 fill,
+        so that a short sample measures the recursion throughput instead of the fixed per-vector starter cost."""
         t = C.c_double(0)
-        _check(lib().orc_time_dos(self.handle, num_moments, num_random, num_threads, C.byref(t)))
+        _check(lib().orc_time_dos(self.handle, num_moments, num_random, num_threads, int(cheap_starter), C.byref(t)))
         return t.value

@@ -112,13 +112,13 @@ class _CudaImpl:
 
     def __init__(self, model, energy_range=(0, 0), kernel=None, matrix_format="ELL", optimal_size=True,
                  interleaved=True, lanczos_precision=0.002, num_threads=0, progress_callback=None,
-                 device=0, max_batch=0):
+                 device=0, max_batch=0, locality_tile=0):
         self._lib = _lib.load()
         kernel = kernel or jackson_kernel()
         emin, emax = (float(energy_range[0]), float(energy_range[1])) if energy_range else (0.0, 0.0)
         cfg = _lib.Config(np.float32(emin), np.float32(emax), kernel.kind, kernel.lambda_value,
                           int(bool(optimal_size)), int(bool(interleaved)), int(matrix_format == "ELL"),
-                          np.float32(lanczos_precision), int(max_batch))
+                          np.float32(lanczos_precision), int(max_batch), int(locality_tile))
         self._handle = C.c_void_p()
         status = self._lib.pbk_create(C.byref(self._handle), int(device), C.byref(cfg))
         _lib.raise_for(status, None)

@@ -106,6 +106,19 @@ int pbk_kernel_required_num_moments(int kernel, double lambda_value, double scal
     return PBK_OK;
 }
 
+int pbk_locality_order(int64_t n, const int32_t* indptr, const int32_t* indices, int32_t tile, int32_t* order) {
+    if (n <= 0 || !indptr || !indices || !order || tile < 1) return PBK_INVALID_ARGUMENT;
+    std::vector<int32_t> queue, rmap;
+    cluster_order(n, indptr, indices, tile, queue, rmap);
+    std::memcpy(order, queue.data(), sizeof(int32_t) * static_cast<size_t>(n));
+    return PBK_OK;
+}
+
+int pbk_mt_jump_window(uint64_t position, uint32_t* window) {
+    if (!window) return PBK_INVALID_ARGUMENT;
+    return mt_jump_window_host(position, window) ? PBK_OK : PBK_RUNTIME_ERROR;
+}
+
 int pbk_moments_dos(pbk_ctx* ctx, int32_t num_moments, int32_t num_random, void* out) {
     return guarded(ctx, [&](Engine& e) { e.moments_dos(num_moments, num_random, static_cast<cd*>(out)); });
 }

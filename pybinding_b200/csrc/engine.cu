@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <thread>
@@ -131,6 +132,16 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     cudaDeviceProp prop{};
     PBK_CUDA(cudaGetDeviceProperties(&prop, device));
     num_sms = prop.multiProcessorCount;
+    // layout / launch tuning: config first, environment overrides for experiments
+    auto env_int = [](char const* name, long fallback) { char const* v = std::getenv(name); return v ? std::strtol(v, nullptr, 10) : fallback; };
+    locality_tile = env_int("PBK_TILE", config.locality_tile);
+    if (locality_tile == 0) locality_tile = 256;
+    if (locality_tile < 0) locality_tile = 0;
+    mt_sequential = env_int("PBK_MT_SEQUENTIAL", 0) != 0;
+    step_tpb = static_cast<int>(env_int("PBK_TPB", 256));
+    step_blocks_per_sm = static_cast<int>(env_int("PBK_BPSM", 0));
+    step_prefetch = static_cast<int>(env_int("PBK_PF", 4));
+    step_prefetch_mask = static_cast<int>(env_int("PBK_PFMASK", 0));
     PBK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (cudaEvent_t* e : {&ev0, &ev1, &ev2, &ev3}) PBK_CUDA(cudaEventCreate(e));
     counter.alloc(64);
@@ -261,15 +272,76 @@ HostEll build_ell_host(int64_t n, const int32_t* indptr, const int32_t* indices,
 
 } // anonymous namespace
 
-void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, bool reorder, Indices const& target) {
+/// Locality ordering for the stochastic (full-system) quantities: the sites are relabelled cluster by cluster,
+/// each cluster a breadth-first ball of at most `tile` sites grown from a seed on the frontier of the clusters
+/// made so far.  A CTA of the step kernel works through one tile of consecutive rows at a time, so the x-rows
+/// it gathers (the ball and a thin halo) stay in that SM's L1 and every x element comes from HBM once.
+/// KPM results are invariant under a relabelling of the sites; the starters are generated per *original* site
+/// index and scattered through the map, exactly like the reference does with its own reorder map
+/// (cppcore/src/kpm/Starter.cpp:68,80).  Fills queue (new -> old) and rmap (old -> new).
+void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int64_t tile,
+                          std::vector<int32_t>& queue, std::vector<int32_t>& rmap) {
+    queue.clear();
+    queue.reserve(n);
+    rmap.assign(n, -1);
+    std::vector<int32_t> seeds;
+    size_t seed_head = 0;
+    int64_t next_unvisited = 0;
+    while (static_cast<int64_t>(queue.size()) < n) {
+        int32_t seed = -1;
+        while (seed_head < seeds.size()) {
+            int32_t const c = seeds[seed_head++];
+            if (rmap[c] < 0) { seed = c; break; }
+        }
+        if (seed_head > (size_t{1} << 22) && seed_head * 2 > seeds.size()) {  // drop the consumed part of the FIFO
+            seeds.erase(seeds.begin(), seeds.begin() + static_cast<std::ptrdiff_t>(seed_head));
+            seed_head = 0;
+        }
+        if (seed < 0) {
+            while (rmap[next_unvisited] >= 0) ++next_unvisited;
+            seed = static_cast<int32_t>(next_unvisited);
+        }
+        size_t const begin = queue.size();
+        size_t const limit = begin + static_cast<size_t>(tile);
+        rmap[seed] = static_cast<int32_t>(queue.size());
+        queue.push_back(seed);
+        size_t head = begin;
+        bool full = false;
+        while (head < queue.size() && !full) {
+            int32_t const row = queue[head];
+            for (int p = indptr[row]; p < indptr[row + 1]; ++p) {
+                int32_t const c = indices[p];
+                if (rmap[c] >= 0) continue;
+                if (queue.size() >= limit) { full = true; break; }
+                rmap[c] = static_cast<int32_t>(queue.size());
+                queue.push_back(c);
+            }
+            if (!full) ++head;
+        }
+        for (size_t q = head; q < queue.size(); ++q) {  // unvisited neighbours of the ball's surface seed later balls
+            int32_t const row = queue[q];
+            for (int p = indptr[row]; p < indptr[row + 1]; ++p) if (rmap[indices[p]] < 0) seeds.push_back(indices[p]);
+        }
+    }
+}
+
+void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int order, Indices const& target) {
     require_hamiltonian();
     PBK_CUDA(cudaSetDevice(device));
     double const t0 = now_seconds();
     Scale const s = scaled ? scaling_factors() : Scale();
     dh = DeviceHamiltonian();
+    bool const reorder = order != ORDER_NATURAL;
 
     std::vector<int32_t> queue;
-    if (reorder) {
+    if (order == ORDER_CLUSTER) {
+        cluster_order(n, h_indptr.data(), h_indices.data(), locality_tile, queue, dh.reorder_map);
+        for (int32_t i : target.src) dh.idx.src.push_back(dh.reorder_map[i]);
+        for (int32_t i : target.dest) dh.idx.dest.push_back(dh.reorder_map[i]);
+        dh.map.data = {static_cast<int32_t>(n)};
+        dh.reordered = true;
+        dh.tile = locality_tile;
+    } else if (order == ORDER_BFS) {
         // BFS relabelling from src[0]; slice k = the k-th shell (OptimizedHamiltonian.cpp:88-143)
         queue.reserve(n);
         queue.push_back(target.src[0]);
@@ -300,6 +372,7 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, bool r
         dh.map.dest_offset = find_offset(dh.idx.dest);
         dh.map.data = std::move(borders);
         dh.reordered = true;
+        dh.sliced = true;
     } else {
         dh.idx = target;
         dh.map.data = {static_cast<int32_t>(n)};
@@ -308,6 +381,7 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, bool r
     HostEll ell;
     const int32_t* q = reorder ? queue.data() : nullptr;
     const int32_t* rm = reorder ? dh.reorder_map.data() : nullptr;
+    if (order == ORDER_CLUSTER) dh.order_queue = queue;  // operators of the same calculation are laid out alike
     switch (dtype) {
         case F32: ell = build_ell_host<float>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const float*>(h_data.data()), scaled, s, q, rm); break;
         case C64: ell = build_ell_host<cf>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cf*>(h_data.data()), scaled, s, q, rm); break;
@@ -336,30 +410,32 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, bool r
 }
 
 DeviceHamiltonian& Engine::natural_hamiltonian() {
-    if (!natural.valid) build_device_hamiltonian(natural, true, false, Indices{{0}, {0}});
+    if (!natural.valid) build_device_hamiltonian(natural, true, locality_tile > 0 ? ORDER_CLUSTER : ORDER_NATURAL, Indices{{0}, {0}});
     return natural;
 }
 
 DeviceHamiltonian& Engine::optimized_for(Indices const& target) {
     if (!config.optimal_size) {  // no light-cone slicing requested: the natural order serves every index
         auto& h = natural_hamiltonian();
-        h.idx = target;
+        h.idx = Indices{};
+        for (int32_t i : target.src) h.idx.src.push_back(h.reordered ? h.reorder_map[i] : i);
+        for (int32_t i : target.dest) h.idx.dest.push_back(h.reordered ? h.reorder_map[i] : i);
         return h;
     }
     if (!(optimized.valid && optimized.original_idx == target)) {  // OptimizedHamiltonian.cpp:43-45
         optimized = DeviceHamiltonian();
-        build_device_hamiltonian(optimized, true, true, target);
+        build_device_hamiltonian(optimized, true, ORDER_BFS, target);
     }
     return optimized;
 }
 
 DeviceHamiltonian& Engine::unscaled_hamiltonian() {
-    if (!unscaled.valid) build_device_hamiltonian(unscaled, false, false, Indices{{0}, {0}});
+    if (!unscaled.valid) build_device_hamiltonian(unscaled, false, ORDER_NATURAL, Indices{{0}, {0}});
     return unscaled;
 }
 
 /// velocity operator V_ij = H_ij * (pos_i - pos_j) on the unscaled H (src/kpm/Moments.cpp:132-156)
-void Engine::upload_operator(DeviceHamiltonian& dh, const float* pos) {
+void Engine::upload_operator(DeviceHamiltonian& dh, const float* pos, DeviceHamiltonian const& like) {
     int64_t const nnz = h_indptr[n];
     std::vector<char> data(static_cast<size_t>(nnz) * dtype_size(dtype));
     auto fill = [&](auto* out, auto const* in) {
@@ -377,13 +453,16 @@ void Engine::upload_operator(DeviceHamiltonian& dh, const float* pos) {
         default: fill(reinterpret_cast<cd*>(data.data()), reinterpret_cast<const cd*>(h_data.data())); break;
     }
     HostEll ell;
+    const int32_t* q = like.reordered ? like.order_queue.data() : nullptr;
+    const int32_t* rm = like.reordered ? like.reorder_map.data() : nullptr;
     switch (dtype) {
-        case F32: ell = build_ell_host<float>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const float*>(data.data()), false, Scale(), nullptr, nullptr); break;
-        case C64: ell = build_ell_host<cf>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cf*>(data.data()), false, Scale(), nullptr, nullptr); break;
-        case F64: ell = build_ell_host<double>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const double*>(data.data()), false, Scale(), nullptr, nullptr); break;
-        default: ell = build_ell_host<cd>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cd*>(data.data()), false, Scale(), nullptr, nullptr); break;
+        case F32: ell = build_ell_host<float>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const float*>(data.data()), false, Scale(), q, rm); break;
+        case C64: ell = build_ell_host<cf>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cf*>(data.data()), false, Scale(), q, rm); break;
+        case F64: ell = build_ell_host<double>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const double*>(data.data()), false, Scale(), q, rm); break;
+        default: ell = build_ell_host<cd>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cd*>(data.data()), false, Scale(), q, rm); break;
     }
     dh = DeviceHamiltonian();
+    dh.tile = like.tile;
     dh.val.alloc(ell.val.size());
     dh.col.alloc(ell.col.size() * sizeof(int32_t));
     PBK_CUDA(cudaMemcpy(dh.val.as(), ell.val.data(), ell.val.size(), cudaMemcpyHostToDevice));
@@ -395,19 +474,23 @@ void Engine::upload_operator(DeviceHamiltonian& dh, const float* pos) {
 }
 
 /// generic operator of KPM.moments(op=...): c128 CSR cast to the Hamiltonian's scalar type (force_cast)
-void Engine::upload_csr_operator(DeviceHamiltonian& dh, int64_t rows, const int32_t* indptr, const int32_t* indices, const cd* data) {
+void Engine::upload_csr_operator(DeviceHamiltonian& dh, int64_t rows, const int32_t* indptr, const int32_t* indices, const cd* data,
+                                 DeviceHamiltonian const& like) {
     int64_t const nnz = indptr[rows];
     HostEll ell;
+    const int32_t* q = like.reordered ? like.order_queue.data() : nullptr;
+    const int32_t* rm = like.reordered ? like.reorder_map.data() : nullptr;
     switch (dtype) {
         case F32: { std::vector<float> d(nnz); for (int64_t i = 0; i < nnz; ++i) d[i] = static_cast<float>(data[i].real());
-                    ell = build_ell_host<float>(rows, indptr, indices, d.data(), false, Scale(), nullptr, nullptr); break; }
+                    ell = build_ell_host<float>(rows, indptr, indices, d.data(), false, Scale(), q, rm); break; }
         case C64: { std::vector<cf> d(nnz); for (int64_t i = 0; i < nnz; ++i) d[i] = cf(static_cast<float>(data[i].real()), static_cast<float>(data[i].imag()));
-                    ell = build_ell_host<cf>(rows, indptr, indices, d.data(), false, Scale(), nullptr, nullptr); break; }
+                    ell = build_ell_host<cf>(rows, indptr, indices, d.data(), false, Scale(), q, rm); break; }
         case F64: { std::vector<double> d(nnz); for (int64_t i = 0; i < nnz; ++i) d[i] = data[i].real();
-                    ell = build_ell_host<double>(rows, indptr, indices, d.data(), false, Scale(), nullptr, nullptr); break; }
-        default: ell = build_ell_host<cd>(rows, indptr, indices, data, false, Scale(), nullptr, nullptr); break;
+                    ell = build_ell_host<double>(rows, indptr, indices, d.data(), false, Scale(), q, rm); break; }
+        default: ell = build_ell_host<cd>(rows, indptr, indices, data, false, Scale(), q, rm); break;
     }
     dh = DeviceHamiltonian();
+    dh.tile = like.tile;
     dh.val.alloc(ell.val.size());
     dh.col.alloc(ell.col.size() * sizeof(int32_t));
     PBK_CUDA(cudaMemcpy(dh.val.as(), ell.val.data(), ell.val.size(), cudaMemcpyHostToDevice));
@@ -572,6 +655,7 @@ void Engine::step(DeviceHamiltonian const& h, const void* x, void* y, void* y2, 
     a.h = h.ell; a.x = x; a.y = y; a.y2 = y2; a.nrows = nrows; a.R = R; a.subtract = subtract; a.sums = sums; a.scale = scale;
     a.partials = partials.as<double>(); a.counter = counter.as<unsigned>(); a.mom = mom.as<double>(); a.m01 = m01.as<double>();
     a.M = M; a.n = nstep; a.fin = fin;
+    a.tile = h.tile; a.tpb = step_tpb; a.blocks_per_sm = step_blocks_per_sm; a.prefetch = step_prefetch; a.prefetch_mask = step_prefetch_mask;
     PBK_CUDA(launch_step(dtype, a, num_sms, stream, nullptr));
     ++launches;
     ++stats.step_launches;
@@ -671,11 +755,15 @@ void Engine::shard(int total, int* first, int* count) const {
 }
 
 void Engine::seed_stream(int64_t skip_vectors) {
-    PBK_CUDA(launch_mt_seed(mt_state.as<uint32_t>(), stream));
-    ++launches;
-    if (skip_vectors > 0) {
-        PBK_CUDA(launch_mt_generate(mt_state.as<uint32_t>(), nullptr, skip_vectors * n * dtype_words(dtype), stream));
+    // position in the reference's single default-seeded stream: vector j owns draws [j*N*w, (j+1)*N*w)
+    stream_pos = static_cast<uint64_t>(skip_vectors) * static_cast<uint64_t>(n) * dtype_words(dtype);
+    if (mt_sequential) {
+        PBK_CUDA(launch_mt_seed(mt_state.as<uint32_t>(), stream));
         ++launches;
+        if (skip_vectors > 0) {
+            PBK_CUDA(launch_mt_generate(mt_state.as<uint32_t>(), nullptr, skip_vectors * n * dtype_words(dtype), stream));
+            ++launches;
+        }
     }
 }
 
@@ -683,10 +771,19 @@ void Engine::generate_random_block(DeviceHamiltonian const& h, int lanes, int R,
     int64_t const words = static_cast<int64_t>(lanes) * n * dtype_words(dtype);
     raw.ensure(sizeof(uint32_t) * words);
     PBK_CUDA(cudaEventRecord(ev0, stream));
-    PBK_CUDA(launch_mt_generate(mt_state.as<uint32_t>(), raw.as<uint32_t>(), words, stream));
+    if (mt_sequential) {
+        PBK_CUDA(launch_mt_generate(mt_state.as<uint32_t>(), raw.as<uint32_t>(), words, stream));
+        ++launches;
+    } else {
+        int nl = 0;
+        mt_states.ensure(sizeof(uint32_t) * mt_stream_scratch_words(MT_MAX_SEGMENTS));
+        PBK_CUDA(launch_mt_stream(mt_states.as<uint32_t>(), MT_MAX_SEGMENTS, stream_pos, words, raw.as<uint32_t>(), stream, &nl));
+        launches += nl;
+    }
+    stream_pos += static_cast<uint64_t>(words);
     PBK_CUDA(launch_random_transform(dtype, raw.as<uint32_t>(), n, R, lanes, h.reordered ? h.perm.as<int32_t>() : nullptr, dst, stream));
     PBK_CUDA(cudaEventRecord(ev1, stream));
-    launches += 2;
+    launches += 1;
     PBK_CUDA(cudaEventSynchronize(ev1));
     float ms = 0;
     PBK_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -783,7 +880,7 @@ void Engine::moments_diagonal(int M, const cd* r0, int count, cd* out) {
         PBK_CUDA(cudaMemsetAsync(vec_a.as(), 0, static_cast<size_t>(n) * R * dtype_size(dtype), stream));
         for (int j = 0; j < lanes; ++j) {
             PBK_CUDA(cudaMemcpyAsync(staging.as(), r0 + static_cast<size_t>(b0 + j) * n, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, stream));
-            PBK_CUDA(launch_scatter_block(dtype, staging.as<double>(), n, R, j, nullptr, vec_a.as(), stream));
+            PBK_CUDA(launch_scatter_block(dtype, staging.as<double>(), n, R, j, h.reordered ? h.perm.as<int32_t>() : nullptr, vec_a.as(), stream));
             PBK_CUDA(cudaStreamSynchronize(stream));
             stats.h2d_bytes += sizeof(double) * 2 * n;
         }
@@ -805,7 +902,7 @@ void Engine::random_vectors(int count, cd* out) {
     seed_stream(0);
     for (int j = 0; j < count; ++j) {
         generate_random_block(h, 1, 1, vec_a.as());
-        PBK_CUDA(launch_extract_lane(dtype, vec_a.as(), n, 1, 0, staging.as<double>(), stream));
+        PBK_CUDA(launch_extract_lane(dtype, vec_a.as(), n, 1, 0, h.reordered ? h.perm.as<int32_t>() : nullptr, staging.as<double>(), stream));
         PBK_CUDA(cudaMemcpyAsync(out + static_cast<size_t>(j) * n, staging.as(), sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, stream));
         PBK_CUDA(cudaStreamSynchronize(stream));
     }
@@ -817,7 +914,7 @@ void Engine::moments_ldos(int M, const int32_t* idx, int nidx, cd* out) {
     for (int i = 0; i < nidx; ++i) if (idx[i] < 0 || idx[i] >= n) throw Error(PBK_INVALID_ARGUMENT, "LDOS index out of range");
     Indices target{std::vector<int32_t>(idx, idx + nidx), std::vector<int32_t>(idx, idx + nidx)};
     auto& h = optimized_for(target);
-    bool const opt = config.optimal_size != 0 && h.reordered;
+    bool const opt = config.optimal_size != 0 && h.sliced;
     reset_stats(M, h, opt, nidx);
     begin_moments();
     progress(-1, nidx);
@@ -866,7 +963,7 @@ void Engine::moments_greens(int M, int row, const int32_t* cols, int ncols, cd* 
     if (ncols < 1) throw Error(PBK_INVALID_ARGUMENT, "at least one column index is required");
     Indices target{{row}, std::vector<int32_t>(cols, cols + ncols)};
     auto& h = optimized_for(target);
-    bool const opt = config.optimal_size != 0 && h.reordered;
+    bool const opt = config.optimal_size != 0 && h.sliced;
     reset_stats(M, h, opt, 1);
     begin_moments();
     size_t const vbytes = static_cast<size_t>(n) * lane_pad(1) * dtype_size(dtype);
@@ -905,8 +1002,8 @@ void Engine::moments_kubo(int M, const float* left, const float* right, int num_
     auto& h = natural_hamiltonian();
     reset_stats(M, h, false, num_random);
     DeviceHamiltonian vl, vr;
-    upload_operator(vl, left);
-    upload_operator(vr, right);
+    upload_operator(vl, left, h);
+    upload_operator(vr, right, h);
     int const s = dtype_size(dtype);
     size_t const vbytes = static_cast<size_t>(n) * s;
     size_t const stack_bytes = vbytes * M;
@@ -984,7 +1081,7 @@ void Engine::core_moments(int num_moments, const cd* alpha, const cd* beta, int6
     } else {                      // Core.cpp:50-55, GenericCollector
         reset_stats(M, h, false, 1);
         DeviceHamiltonian op;
-        if (op_rows != 0) upload_csr_operator(op, op_rows, op_indptr, op_indices, op_data);
+        if (op_rows != 0) upload_csr_operator(op, op_rows, op_indptr, op_indices, op_data, h);
         begin_moments();
         size_t const vbytes = static_cast<size_t>(n) * dtype_size(dtype);
         vec_a.ensure(vbytes);
@@ -993,10 +1090,10 @@ void Engine::core_moments(int num_moments, const cd* alpha, const cd* beta, int6
         ensure_moment_buffers(1, M);
         DevBuf staging(sizeof(double) * 2 * n), beta_dev(vbytes);
         PBK_CUDA(cudaMemcpyAsync(staging.as(), beta ? beta : alpha, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, stream));
-        PBK_CUDA(launch_scatter_block(dtype, staging.as<double>(), n, 1, 0, nullptr, beta_dev.as(), stream));
+        PBK_CUDA(launch_scatter_block(dtype, staging.as<double>(), n, 1, 0, h.reordered ? h.perm.as<int32_t>() : nullptr, beta_dev.as(), stream));
         PBK_CUDA(cudaStreamSynchronize(stream));
         PBK_CUDA(cudaMemcpyAsync(staging.as(), alpha, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, stream));
-        PBK_CUDA(launch_scatter_block(dtype, staging.as<double>(), n, 1, 0, nullptr, vec_a.as(), stream));
+        PBK_CUDA(launch_scatter_block(dtype, staging.as<double>(), n, 1, 0, h.reordered ? h.perm.as<int32_t>() : nullptr, vec_a.as(), stream));
         stats.h2d_bytes += 2 * sizeof(double) * 2 * n;
         run_offdiagonal(h, M, false, [&](int k, void* r, double scale) {
             const void* v = r;

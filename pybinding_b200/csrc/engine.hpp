@@ -69,9 +69,14 @@ struct Indices {
 };
 
 /// Device-resident scaled (and optionally BFS-reordered) Hamiltonian in slot-major ELL
+enum OrderMode : int { ORDER_NATURAL = 0, ORDER_BFS = 1, ORDER_CLUSTER = 2 };
+
 struct DeviceHamiltonian {
     bool valid = false;
-    bool reordered = false;
+    bool reordered = false;        // rows are relabelled: reorder_map / perm are set
+    bool sliced = false;           // BFS order from the source: `map` holds the light-cone slices
+    int64_t tile = 0;              // ORDER_CLUSTER: rows per locality cluster (the step kernel's CTA tile), else 0
+    std::vector<int32_t> order_queue;  // device row -> original (ORDER_CLUSTER only)
     Indices original_idx, idx;     // idx: positions in the device ordering
     SliceMap map;
     std::vector<int32_t> reorder_map;  // original -> device row (empty: identity)
@@ -154,6 +159,8 @@ private:
     // ---- configuration / device ----
     int device = 0;
     int num_sms = 148;
+    int step_tpb = 256, step_blocks_per_sm = 0, step_prefetch = 0, step_prefetch_mask = 0;
+    int64_t locality_tile = 0;   // rows per locality cluster of the full-system layout (0: keep the caller's order)
     pbk_config config{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -179,7 +186,10 @@ private:
     DeviceHamiltonian unscaled;   // original values, original order (Lanczos)
 
     // ---- work buffers ----
-    DevBuf vec_a, vec_b, vec_t, raw, mom, m01, acc, partials, counter, scratch, mt_state, idx_buf;
+    DevBuf vec_a, vec_b, vec_t, raw, mom, m01, acc, partials, counter, scratch, mt_state, mt_states, idx_buf;
+    static constexpr int MT_MAX_SEGMENTS = 2048;
+    uint64_t stream_pos = 0;     // next draw of the reference's random stream
+    bool mt_sequential = false;  // PBK_MT_SEQUENTIAL=1: single-CTA generator (cross-check of the jump-ahead path)
 
     // ---- multi-GPU ----
     std::unique_ptr<NcclApi> nccl;
@@ -192,12 +202,13 @@ private:
     // ---- helpers ----
     void require_hamiltonian() const;
     void compute_bounds();
-    void build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, bool reorder, Indices const& target);
+    void build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int order, Indices const& target);
     DeviceHamiltonian& natural_hamiltonian();
     DeviceHamiltonian& optimized_for(Indices const& target);
     DeviceHamiltonian& unscaled_hamiltonian();
-    void upload_operator(DeviceHamiltonian& dh, const float* positions);  // velocity operator (natural order)
-    void upload_csr_operator(DeviceHamiltonian& dh, int64_t rows, const int32_t* indptr, const int32_t* indices, const cd* data);
+    void upload_operator(DeviceHamiltonian& dh, const float* positions, DeviceHamiltonian const& like);  // velocity operator
+    void upload_csr_operator(DeviceHamiltonian& dh, int64_t rows, const int32_t* indptr, const int32_t* indices, const cd* data,
+                             DeviceHamiltonian const& like);
 
     int pick_batch(int vectors, int extra_blocks) const;
     int lane_pad(int R) const;
@@ -221,6 +232,10 @@ private:
     double moments_wall0 = 0;
     int64_t launches = 0;
 };
+
+/// locality relabelling of the full-system layout (engine.cu)
+void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int64_t tile,
+                   std::vector<int32_t>& queue, std::vector<int32_t>& rmap);
 
 // kernels (src/kpm/Kernel.cpp:6-49)
 int round_num_moments(int n);

@@ -23,6 +23,9 @@
 #include "kernels.cuh"
 
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace pbk {
 
@@ -104,26 +107,39 @@ template<class CH> __device__ __forceinline__ void store_(CH* p, CH const& v) {
     else if constexpr (sizeof(CH) == 8) { *reinterpret_cast<int2*>(p) = *reinterpret_cast<const int2*>(&v); }
     else { *reinterpret_cast<int*>(p) = *reinterpret_cast<const int*>(&v); }
 }
+template<class CH> __device__ __forceinline__ void store_cs(CH* p, CH const& v) {  // streaming store: not re-read by this launch
+    if constexpr (sizeof(CH) == 16) { __stcs(reinterpret_cast<int4*>(p), *reinterpret_cast<const int4*>(&v)); }
+    else if constexpr (sizeof(CH) == 8) { __stcs(reinterpret_cast<int2*>(p), *reinterpret_cast<const int2*>(&v)); }
+    else { __stcs(reinterpret_cast<int*>(p), *reinterpret_cast<const int*>(&v)); }
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template<class T> __device__ __forceinline__ T ldg_scalar(const T* p) {
     Chunk<T, 1> c = load_nc(reinterpret_cast<const Chunk<T, 1>*>(p));
     return c.e[0];
 }
 
-constexpr int MAX_TPB = 256;
-
 struct StepDev {  // POD copy of StepArgs for the kernel
     const void* val; const int32_t* col; int64_t pitch; int k;
     const void* x; void* y; void* y2;
     int64_t nrows; int R; int cpr; int rpb;
+    int ipt; int64_t tile_jump;   // block-iterations per tile; rows to skip to reach this block's next tile
+    int pf;                       // L2 prefetch distance of the streamed operands, in block-iterations (0: off)
+    int pfmask;                   // only chunks with (tx & pfmask) == 0 issue the prefetch (one request per line)
     double scale;
     double* partials; unsigned* counter; double* mom; double* m01; int M; int n; int fin;
 };
 
 // ------------------------------------------------------------------------------------------------
 // The fused step kernel.  K > 0: ELL width known at compile time (unrolled + prefetched); K == 0: generic.
+//
+// Row -> CTA mapping: the rows are cut into tiles of ipt * rpb consecutive rows and tile t belongs to CTA
+// t mod gridDim.x, which walks through it rpb rows at a time.  With the engine's locality ordering a tile is
+// a breadth-first ball of the lattice, so the x-rows gathered by a CTA are re-used from the SM's L1 (each
+// x-row is needed by its own row and by every neighbour) instead of being re-read from L2 by other SMs.
+// ipt == 1 degenerates to a plain grid-stride loop (used for the light-cone-sliced runs).
 // ------------------------------------------------------------------------------------------------
-template<class T, int V, int K, bool SUB, bool SUMS>
-__global__ void __launch_bounds__(MAX_TPB) cheb_step(StepDev a) {
+template<class T, int V, int K, bool SUB, bool SUMS, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) cheb_step(StepDev a) {
     using CH = Chunk<T, V>;
     constexpr int C = ST<T>::C;
     constexpr int NACC = V * C;
@@ -138,8 +154,37 @@ __global__ void __launch_bounds__(MAX_TPB) cheb_step(StepDev a) {
     int const cpr = a.cpr;                       // 16-byte chunks per row
     int const tx = threadIdx.x % cpr;            // chunk within the row
     int const ty = threadIdx.x / cpr;            // row within the block
-    int64_t const stride = static_cast<int64_t>(gridDim.x) * a.rpb;
-    int64_t row = static_cast<int64_t>(blockIdx.x) * a.rpb + ty;
+    int const rpb = a.rpb;
+    int const ipt = a.ipt;
+    int64_t const tile_jump = a.tile_jump;
+    int64_t row = static_cast<int64_t>(blockIdx.x) * ipt * rpb + ty;
+    int w = 0;                                   // block-iteration within the current tile
+    auto advance = [&](int64_t r) {
+        r += rpb;
+        if (++w == ipt) { w = 0; r += tile_jump; }
+        return r;
+    };
+
+    // L2 prefetch cursor: runs `pf` block-iterations ahead of `row` along the same row sequence.  The streamed
+    // operands (y and the tile's own x rows) are then L2 hits when the demand loads arrive, so the DRAM
+    // queue depth no longer depends on how many loads the register file can keep in flight.
+    int64_t prow = row;
+    int pw = 0;
+    auto advance_pf = [&](int64_t r) {
+        r += rpb;
+        if (++pw == ipt) { pw = 0; r += tile_jump; }
+        return r;
+    };
+    bool const pf_lane = (tx & a.pfmask) == 0;
+    if (a.pf > 0) {
+        for (int i = 0; i < a.pf; ++i) {
+            if (prow < a.nrows && pf_lane) {
+                prefetch_l2(x + prow * cpr + tx);
+                if constexpr (SUB) prefetch_l2(y + prow * cpr + tx);
+            }
+            prow = advance_pf(prow);
+        }
+    }
 
     double acc[NACC];
 #pragma unroll
@@ -152,7 +197,14 @@ __global__ void __launch_bounds__(MAX_TPB) cheb_step(StepDev a) {
             for (int s = 0; s < KK; ++s) { c[s] = __ldg(col + s * a.pitch + row); v[s] = ldg_scalar(val + s * a.pitch + row); }
         }
         while (row < a.nrows) {
-            int64_t const next = row + stride;
+            int64_t const next = advance(row);
+            if (a.pf > 0) {
+                if (prow < a.nrows && pf_lane) {
+                    prefetch_l2(x + prow * cpr + tx);
+                    if constexpr (SUB) prefetch_l2(y + prow * cpr + tx);
+                }
+                prow = advance_pf(prow);
+            }
             // gathers of the current row (independent loads, all in flight together)
             CH xg[KK];
 #pragma unroll
@@ -176,14 +228,14 @@ __global__ void __launch_bounds__(MAX_TPB) cheb_step(StepDev a) {
                 out.e[e] = r;
                 if constexpr (SUMS) sums_(acc + e * C, xr.e[e], r);
             }
-            store_(y + row * cpr + tx, out);
-            if (y2) store_(y2 + row * cpr + tx, out);
+            store_cs(y + row * cpr + tx, out);
+            if (y2) store_cs(y2 + row * cpr + tx, out);
 #pragma unroll
             for (int s = 0; s < KK; ++s) { c[s] = cn[s]; v[s] = vn[s]; }
             row = next;
         }
     } else {
-        for (; row < a.nrows; row += stride) {
+        for (; row < a.nrows; row = advance(row)) {
             CH out;
 #pragma unroll
             for (int e = 0; e < V; ++e) out.e[e] = zero_(T{});
@@ -208,32 +260,30 @@ __global__ void __launch_bounds__(MAX_TPB) cheb_step(StepDev a) {
 #pragma unroll
                 for (int e = 0; e < V; ++e) sums_(acc + e * C, xr.e[e], out.e[e]);
             }
-            store_(y + row * cpr + tx, out);
-            if (y2) store_(y2 + row * cpr + tx, out);
+            store_cs(y + row * cpr + tx, out);
+            if (y2) store_cs(y2 + row * cpr + tx, out);
         }
     }
 
     if constexpr (SUMS) {
-        // ---- block reduction over the rows of the block (tree over ty, fixed order) ----
-        __shared__ double sm[MAX_TPB * NACC];
+        // ---- block reduction over the rows of the block: one value at a time through a TPB-sized buffer
+        //      (fixed-order tree over ty); a small static footprint keeps the SM's L1 carve-out large ----
+        __shared__ double sm[TPB];
         __shared__ bool is_last;
         int const tid = threadIdx.x;
-#pragma unroll
-        for (int q = 0; q < NACC; ++q) sm[tid * NACC + q] = acc[q];
         int p2 = 1;
-        while (p2 < a.rpb) p2 <<= 1;
-        for (int s = p2 >> 1; s > 0; s >>= 1) {
-            __syncthreads();
-            if (ty < s && ty + s < a.rpb) {
-#pragma unroll
-                for (int q = 0; q < NACC; ++q) sm[tid * NACC + q] += sm[(tid + s * cpr) * NACC + q];
-            }
-        }
-        __syncthreads();
+        while (p2 < rpb) p2 <<= 1;
         int const RC = a.R * C;
-        if (ty == 0) {
 #pragma unroll
-            for (int q = 0; q < NACC; ++q) a.partials[static_cast<int64_t>(blockIdx.x) * RC + tx * NACC + q] = sm[tx * NACC + q];
+        for (int q = 0; q < NACC; ++q) {
+            sm[tid] = acc[q];
+            for (int s = p2 >> 1; s > 0; s >>= 1) {
+                __syncthreads();
+                if (ty < s && ty + s < rpb) sm[tid] += sm[tid + s * cpr];
+            }
+            __syncthreads();
+            if (ty == 0) a.partials[static_cast<int64_t>(blockIdx.x) * RC + tx * NACC + q] = sm[tx];
+            __syncthreads();
         }
         __threadfence();
         __syncthreads();
@@ -282,47 +332,82 @@ __global__ void __launch_bounds__(MAX_TPB) cheb_step(StepDev a) {
     }
 }
 
-template<class T, int V, int K>
-cudaError_t launch_step_vk(StepDev const& d, bool sub, bool sums, int grid, int block, cudaStream_t stream) {
-    if (sub && sums) cheb_step<T, V, K, true, true><<<grid, block, 0, stream>>>(d);
-    else if (sub) cheb_step<T, V, K, true, false><<<grid, block, 0, stream>>>(d);
-    else if (sums) cheb_step<T, V, K, false, true><<<grid, block, 0, stream>>>(d);
-    else cheb_step<T, V, K, false, false><<<grid, block, 0, stream>>>(d);
-    return cudaGetLastError();
+using StepKernel = void (*)(StepDev);
+
+template<class T, int V, int K, int TPB, int MINB>
+StepKernel step_kernel_vk(bool sub, bool sums) {
+    if (sub && sums) return cheb_step<T, V, K, true, true, TPB, MINB>;
+    if (sub) return cheb_step<T, V, K, true, false, TPB, MINB>;
+    if (sums) return cheb_step<T, V, K, false, true, TPB, MINB>;
+    return cheb_step<T, V, K, false, false, TPB, MINB>;
 }
 
-template<class T, int V>
-cudaError_t launch_step_v(StepDev const& d, bool sub, bool sums, int grid, int block, cudaStream_t stream, int* kused) {
-    switch (d.k) {
-        case 3: *kused = 3; return launch_step_vk<T, V, 3>(d, sub, sums, grid, block, stream);
-        case 4: *kused = 4; return launch_step_vk<T, V, 4>(d, sub, sums, grid, block, stream);
-        case 7: *kused = 7; return launch_step_vk<T, V, 7>(d, sub, sums, grid, block, stream);
-        default: *kused = 0; return launch_step_vk<T, V, 0>(d, sub, sums, grid, block, stream);
+template<class T, int V, int TPB, int MINB>
+StepKernel step_kernel_v(int k, bool sub, bool sums, int* kused) {
+    switch (k) {
+        case 3: *kused = 3; return step_kernel_vk<T, V, 3, TPB, MINB>(sub, sums);
+        case 4: *kused = 4; return step_kernel_vk<T, V, 4, TPB, MINB>(sub, sums);
+        case 7: *kused = 7; return step_kernel_vk<T, V, 7, TPB, MINB>(sub, sums);
+        default: *kused = 0; return step_kernel_vk<T, V, 0, TPB, MINB>(sub, sums);
     }
 }
 
-template<class T>
+/// resident CTAs per SM of a kernel variant (queried once per variant and block size)
+int resident_blocks(StepKernel fn, int block) {
+    static std::mutex mutex;
+    static std::map<std::pair<StepKernel, int>, int> cache;
+    std::lock_guard<std::mutex> lock(mutex);
+    auto const key = std::make_pair(fn, block);
+    auto const it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, block, 0) != cudaSuccess || nb < 1) nb = 1;
+    cache[key] = nb;
+    return nb;
+}
+
+template<class T, int TPB, int MINB>
 cudaError_t launch_step_t(StepArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info) {
     constexpr int VMAX = 16 / sizeof(T);
     int V = VMAX;
     while (V > 1 && a.R % V != 0) V >>= 1;
     if (VMAX == 4 && V == 2) V = 1;  // only the full-width and the scalar variants are instantiated
     int const cpr = a.R / V;
-    if (cpr > MAX_TPB) return cudaErrorInvalidValue;
-    int const rpb = MAX_TPB / cpr;
+    if (cpr > TPB) return cudaErrorInvalidValue;
+    int const rpb = TPB / cpr;
     int const block = rpb * cpr;
-    int64_t const need = (a.nrows + rpb - 1) / rpb;
-    int grid = static_cast<int>(need < static_cast<int64_t>(max_step_blocks(num_sms)) ? need : max_step_blocks(num_sms));
-    if (grid < 1) grid = 1;
-
-    StepDev d{a.h.val, a.h.col, a.h.pitch, a.h.k, a.x, a.y, a.y2, a.nrows, a.R, cpr, rpb, a.scale,
-              a.partials, a.counter, a.mom, a.m01, a.M, a.n, a.fin};
     int kused = 0;
-    cudaError_t err;
-    if (V == VMAX && VMAX > 1) err = launch_step_v<T, VMAX>(d, a.subtract, a.sums, grid, block, stream, &kused);
-    else err = launch_step_v<T, 1>(d, a.subtract, a.sums, grid, block, stream, &kused);
+    StepKernel const fn = (V == VMAX && VMAX > 1) ? step_kernel_v<T, VMAX, TPB, MINB>(a.h.k, a.subtract, a.sums, &kused)
+                                                  : step_kernel_v<T, 1, TPB, MINB>(a.h.k, a.subtract, a.sums, &kused);
+    int ipt = 1;
+    if (a.tile > rpb) ipt = static_cast<int>((a.tile + rpb - 1) / rpb);
+    int64_t const tile_rows = static_cast<int64_t>(ipt) * rpb;
+    int64_t const need = (a.nrows + tile_rows - 1) / tile_rows;
+    // persistent grid: exactly the CTAs that are resident at once, so all of them sweep the rows together
+    int const cap = num_sms * (a.blocks_per_sm > 0 ? a.blocks_per_sm : resident_blocks(fn, block));
+    int grid = static_cast<int>(need < static_cast<int64_t>(cap) ? need : cap);
+    if (grid < 1) grid = 1;
+    if (grid > max_step_blocks(num_sms)) grid = max_step_blocks(num_sms);
+
+    StepDev d{a.h.val, a.h.col, a.h.pitch, a.h.k, a.x, a.y, a.y2, a.nrows, a.R, cpr, rpb,
+              ipt, static_cast<int64_t>(grid - 1) * tile_rows, a.prefetch, a.prefetch_mask, a.scale,
+              a.partials, a.counter, a.mom, a.m01, a.M, a.n, a.fin};
+    fn<<<grid, block, 0, stream>>>(d);
     if (info) { info->grid = grid; info->block = block; info->V = V; info->K = kused; }
-    return err;
+    return cudaGetLastError();
+}
+
+template<class T>
+cudaError_t launch_step_tpb(StepArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info) {
+    switch (a.tpb) {
+        case 512: return launch_step_t<T, 512, 2>(a, num_sms, stream, info);
+        case 1024: return launch_step_t<T, 1024, 1>(a, num_sms, stream, info);
+        case 2565: return launch_step_t<T, 256, 5>(a, num_sms, stream, info);  // experiments: 256 threads, >= 5/6/8 CTAs per SM
+        case 2566: return launch_step_t<T, 256, 6>(a, num_sms, stream, info);
+        case 2568: return launch_step_t<T, 256, 8>(a, num_sms, stream, info);
+        case 2563: return launch_step_t<T, 256, 3>(a, num_sms, stream, info);
+        default: return launch_step_t<T, 256, 4>(a, num_sms, stream, info);
+    }
 }
 
 } // anonymous namespace
@@ -332,10 +417,10 @@ int max_step_blocks(int num_sms) { return num_sms * 8; }
 cudaError_t launch_step(int dtype, StepArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info) {
     if (a.nrows <= 0) return cudaSuccess;
     switch (dtype) {
-        case F32: return launch_step_t<float>(a, num_sms, stream, info);
-        case C64: return launch_step_t<float2>(a, num_sms, stream, info);
-        case F64: return launch_step_t<double>(a, num_sms, stream, info);
-        case C128: return launch_step_t<double2>(a, num_sms, stream, info);
+        case F32: return launch_step_tpb<float>(a, num_sms, stream, info);
+        case C64: return launch_step_tpb<float2>(a, num_sms, stream, info);
+        case F64: return launch_step_tpb<double>(a, num_sms, stream, info);
+        case C128: return launch_step_tpb<double2>(a, num_sms, stream, info);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -447,10 +532,11 @@ __global__ void scatter_block_kernel(const double* src, int64_t n, int R, int la
 }
 
 template<class T>
-__global__ void extract_lane_kernel(const T* v, int64_t n, int R, int lane, double* out) {
+__global__ void extract_lane_kernel(const T* v, int64_t n, int R, int lane, const int32_t* perm, double* out) {
     int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    T const e = v[i * R + lane];
+    int64_t const row = perm ? perm[i] : i;
+    T const e = v[row * R + lane];
     out[2 * i] = re_(e); out[2 * i + 1] = im_(e);
 }
 
@@ -531,9 +617,9 @@ cudaError_t launch_scatter_block(int dtype, const double* src_c128, int64_t n, i
     return cudaGetLastError();
 }
 
-cudaError_t launch_extract_lane(int dtype, const void* v, int64_t n, int R, int lane, double* out_c128, cudaStream_t s) {
+cudaError_t launch_extract_lane(int dtype, const void* v, int64_t n, int R, int lane, const int32_t* perm_dev, double* out_c128, cudaStream_t s) {
     int const grid = static_cast<int>((n + 255) / 256);
-    PBK_DISPATCH(dtype, (extract_lane_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(v), n, R, lane, out_c128)));
+    PBK_DISPATCH(dtype, (extract_lane_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(v), n, R, lane, perm_dev, out_c128)));
     return cudaGetLastError();
 }
 
