@@ -97,6 +97,8 @@ typedef struct pbk_stats {
     int64_t d2h_bytes;
     int32_t batch;            /* vectors per pass used by the last calculation */
     int32_t num_batches;
+    double moments_device_ms; /* device time of the whole moments phase (CUDA events on the library stream, from the
+                                 first starter kernel to the moment copy-out, allreduce included) */
 } pbk_stats;
 
 /* Progress protocol of DefaultCompute (cppcore/src/kpm/default/Compute.cpp:133-145):

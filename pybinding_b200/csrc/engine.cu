@@ -143,7 +143,7 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     step_prefetch = static_cast<int>(env_int("PBK_PF", 4));
     step_prefetch_mask = static_cast<int>(env_int("PBK_PFMASK", 0));
     PBK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : {&ev0, &ev1, &ev2, &ev3}) PBK_CUDA(cudaEventCreate(e));
+    for (cudaEvent_t* e : {&ev0, &ev1, &ev2, &ev3, &ev_begin, &ev_end}) PBK_CUDA(cudaEventCreate(e));
     counter.alloc(64);
     PBK_CUDA(cudaMemset(counter.as(), 0, 64));
     mt_state.alloc(sizeof(uint32_t) * (MT_N + 8));
@@ -152,7 +152,7 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
 Engine::~Engine() {
     cudaSetDevice(device);
     comm_destroy();
-    for (cudaEvent_t e : {ev0, ev1, ev2, ev3}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ev0, ev1, ev2, ev3, ev_begin, ev_end}) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -738,10 +738,15 @@ void Engine::reset_stats(int M, DeviceHamiltonian const& h, bool opt_size, doubl
 void Engine::begin_moments() {
     PBK_CUDA(cudaSetDevice(device));
     moments_wall0 = now_seconds();
+    PBK_CUDA(cudaEventRecord(ev_begin, stream));
 }
 
 void Engine::end_moments() {
+    PBK_CUDA(cudaEventRecord(ev_end, stream));
     PBK_CUDA(cudaStreamSynchronize(stream));
+    float device_ms = 0;
+    PBK_CUDA(cudaEventElapsedTime(&device_ms, ev_begin, ev_end));
+    stats.moments_device_ms += device_ms;
     stats.moments_time += now_seconds() - moments_wall0;
     stats.kernel_launches = launches;
     stats.eps = stats.moments_time > 0 ? stats.multiplier * static_cast<double>(stats.opt_nnz) / stats.moments_time : 0;

@@ -163,7 +163,7 @@ private:
     int64_t locality_tile = 0;   // rows per locality cluster of the full-system layout (0: keep the caller's order)
     pbk_config config{};
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_begin = nullptr, ev_end = nullptr;
     pbk_progress_fn progress_fn = nullptr;
     void* progress_user = nullptr;
 
