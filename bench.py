@@ -203,9 +203,8 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    import ctypes as C
     import pybinding_b200 as pb
-    from pybinding_b200 import _lib
+    from pybinding_b200 import multigpu
 
     model = build_model(w)
     nnz, n = model.hamiltonian.nnz, model.hamiltonian.shape[0]
@@ -214,15 +213,7 @@ def main():
     def make_kpm():
         k = pb.kpm(model, energy_range=w["energy_range"], silent=True, device=local_rank, max_batch=args.max_batch)
         if world > 1:
-            import torch
-            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                buf = C.create_string_buffer(128)
-                status = _lib.load().pbk_comm_unique_id(buf)
-                assert status == 0, _lib.load().pbk_last_error(None)
-                uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
-            dist.broadcast(uid, 0)
-            k.impl.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+            multigpu.attach(k, dist, rank, world, "cuda")
         return k
 
     def barrier():

@@ -200,6 +200,10 @@ int pbk_report(pbk_ctx* ctx, int shortform, char* buffer, int64_t size);
 int pbk_comm_unique_id(char id[128]);
 int pbk_comm_init(pbk_ctx* ctx, int32_t world_size, int32_t rank, const char id[128]);
 int pbk_comm_destroy(pbk_ctx* ctx);
+/* The partition every sharded entry point uses: rank `rank` of `world_size` owns units [first, first + count) of `total`
+ * (contiguous blocks, remainder to the lowest ranks).  For stochastic vectors unit j consumes draws [j*N*w, (j+1)*N*w) of
+ * the reference's single MT19937 stream, so the union over ranks is the single-GPU / CPU calculation.  Host-only. */
+int pbk_shard(int32_t total, int32_t world_size, int32_t rank, int32_t* first, int32_t* count);
 
 #ifdef __cplusplus
 }

@@ -114,6 +114,14 @@ int pbk_locality_order(int64_t n, const int32_t* indptr, const int32_t* indices,
     return PBK_OK;
 }
 
+int pbk_shard(int32_t total, int32_t world_size, int32_t rank, int32_t* first, int32_t* count) {
+    if (total < 0 || world_size < 1 || rank < 0 || rank >= world_size || !first || !count) return PBK_INVALID_ARGUMENT;
+    int f = 0, c = 0;
+    shard_range(total, world_size, rank, &f, &c);
+    *first = f; *count = c;
+    return PBK_OK;
+}
+
 int pbk_mt_jump_window(uint64_t position, uint32_t* window) {
     if (!window) return PBK_INVALID_ARGUMENT;
     return mt_jump_window_host(position, window) ? PBK_OK : PBK_RUNTIME_ERROR;

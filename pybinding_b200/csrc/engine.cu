@@ -752,12 +752,14 @@ void Engine::end_moments() {
     stats.eps = stats.moments_time > 0 ? stats.multiplier * static_cast<double>(stats.opt_nnz) / stats.moments_time : 0;
 }
 
-void Engine::shard(int total, int* first, int* count) const {
+void shard_range(int total, int world, int rank, int* first, int* count) {
     // contiguous blocks, remainder to the lowest ranks
     int const base = total / world, rem = total % world;
     *count = base + (rank < rem ? 1 : 0);
     *first = rank * base + std::min(rank, rem);
 }
+
+void Engine::shard(int total, int* first, int* count) const { shard_range(total, world, rank, first, count); }
 
 void Engine::seed_stream(int64_t skip_vectors) {
     // position in the reference's single default-seeded stream: vector j owns draws [j*N*w, (j+1)*N*w)

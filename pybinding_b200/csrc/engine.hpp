@@ -233,6 +233,9 @@ private:
     int64_t launches = 0;
 };
 
+/// units [first, first + count) of `total` owned by `rank` (engine.cu)
+void shard_range(int total, int world, int rank, int* first, int* count);
+
 /// locality relabelling of the full-system layout (engine.cu)
 void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int64_t tile,
                    std::vector<int32_t>& queue, std::vector<int32_t>& rmap);
