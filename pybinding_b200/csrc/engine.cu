@@ -142,6 +142,8 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     step_blocks_per_sm = static_cast<int>(env_int("PBK_BPSM", 0));
     step_prefetch = static_cast<int>(env_int("PBK_PF", 4));
     step_prefetch_mask = static_cast<int>(env_int("PBK_PFMASK", 0));
+    bulk_stages = static_cast<int>(env_int("PBK_BULK", 4));
+    bulk_xstage = env_int("PBK_XS", 1) != 0;
     PBK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (cudaEvent_t* e : {&ev0, &ev1, &ev2, &ev3, &ev_begin, &ev_end}) PBK_CUDA(cudaEventCreate(e));
     counter.alloc(64);
@@ -398,12 +400,16 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
         PBK_CUDA(cudaMemcpyAsync(dh.perm.as(), dh.reorder_map.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream));
         stats.h2d_bytes += static_cast<int64_t>(sizeof(int32_t) * n);
     }
-    PBK_CUDA(cudaStreamSynchronize(stream));
     dh.ell.val = dh.val.as();
     dh.ell.col = dh.col.as<int32_t>();
     dh.ell.rows = n;
     dh.ell.pitch = ell.pitch;
     dh.ell.k = ell.k;
+    if (order == ORDER_CLUSTER && bulk_stages >= 2) {  // row-major records for the bulk-copy staged step kernel
+        dh.packed.alloc(packed_ell_bytes(dtype, dh.ell));
+        PBK_CUDA(launch_pack_ell(dtype, dh.ell, dh.packed.as(), stream));
+    }
+    PBK_CUDA(cudaStreamSynchronize(stream));
     dh.original_idx = target;
     dh.valid = true;
     dh.seconds = now_seconds() - t0;
@@ -656,9 +662,12 @@ void Engine::step(DeviceHamiltonian const& h, const void* x, void* y, void* y2, 
     a.partials = partials.as<double>(); a.counter = counter.as<unsigned>(); a.mom = mom.as<double>(); a.m01 = m01.as<double>();
     a.M = M; a.n = nstep; a.fin = fin;
     a.tile = h.tile; a.tpb = step_tpb; a.blocks_per_sm = step_blocks_per_sm; a.prefetch = step_prefetch; a.prefetch_mask = step_prefetch_mask;
-    PBK_CUDA(launch_step(dtype, a, num_sms, stream, nullptr));
+    a.packed = h.packed.bytes() ? h.packed.as() : nullptr; a.bulk_stages = bulk_stages; a.bulk_xstage = bulk_xstage;
+    LaunchInfo info;
+    PBK_CUDA(launch_step(dtype, a, num_sms, stream, &info));
     ++launches;
     ++stats.step_launches;
+    if (info.bulk) ++stats.bulk_launches;
     int const s = dtype_size(dtype);
     stats.step_bytes += static_cast<double>(nrows) * (h.ell.k * (s + 4.0) + static_cast<double>(R) * s * (2 + (subtract ? 1 : 0) + (y2 ? 1 : 0)));
 }

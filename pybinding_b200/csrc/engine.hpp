@@ -81,6 +81,7 @@ struct DeviceHamiltonian {
     SliceMap map;
     std::vector<int32_t> reorder_map;  // original -> device row (empty: identity)
     DevBuf val, col, perm;
+    DevBuf packed;                 // row-major packed copy of the ELL arrays for the bulk-copy staged step kernel (ORDER_CLUSTER only)
     EllDev ell;
     double seconds = 0;
     uint64_t memory() const { return static_cast<uint64_t>(ell.rows) * ell.k * 0 + val.bytes() + col.bytes(); }
@@ -160,6 +161,8 @@ private:
     int device = 0;
     int num_sms = 148;
     int step_tpb = 256, step_blocks_per_sm = 0, step_prefetch = 0, step_prefetch_mask = 0;
+    int bulk_stages = 4;         // pipeline depth of the bulk-copy staged step kernel (0: general kernel only)
+    bool bulk_xstage = true;     // staged kernel: the CTA's own x rows go through shared memory too
     int64_t locality_tile = 0;   // rows per locality cluster of the full-system layout (0: keep the caller's order)
     pbk_config config{};
     cudaStream_t stream = nullptr;

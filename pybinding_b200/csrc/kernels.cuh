@@ -46,12 +46,24 @@ struct StepArgs {
     int blocks_per_sm = 0;       // 0: as many as are resident
     int prefetch = 0;            // L2 prefetch distance in block-iterations (0: off)
     int prefetch_mask = 0;       // chunks with (index & mask) == 0 issue the prefetch
+    // bulk-copy (TMA) staged variant, kernels_bulk.cu
+    const void* packed = nullptr;  // row-major packed copy of h (launch_pack_ell); required by the staged variant
+    int bulk_stages = 0;         // >= 2: use the staged variant with this pipeline depth where it applies
+    bool bulk_xstage = true;     // stage the CTA's own x rows too (else: L2 bulk prefetch + read through L1)
 };
 
-struct LaunchInfo { int grid = 0, block = 0, V = 0, K = 0; };
+struct LaunchInfo { int grid = 0, block = 0, V = 0, K = 0, bulk = 0; };
 
 /// Fused Chebyshev step (K1/K2/K3).  Returns the launch geometry used (for stats / tests).
 cudaError_t launch_step(int dtype, StepArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info);
+/// Staged variant (kernels_bulk.cu): *handled == false means "not applicable, use the general kernel".
+cudaError_t launch_step_bulk(int dtype, StepArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info, bool* handled);
+/// Row-major packed copy of an ELL matrix for the staged variant: per row int32 col[k] (padded to 8 / 16 bytes), then
+/// val[k]; `rec` bytes per row (a multiple of 16), PACKED_PAD_ROWS zero records after the last row so whole blocks can always be copied.
+constexpr int PACKED_PAD_ROWS = 256;
+void packed_record_layout(int scalar_bytes, int k, uint32_t* rec, uint32_t* valoff);
+size_t packed_ell_bytes(int dtype, EllDev const& h);
+cudaError_t launch_pack_ell(int dtype, EllDev const& h, void* packed, cudaStream_t s);
 /// Upper bound of blocks launch_step may use (size of the partials buffer = this * R * 3 doubles)
 int max_step_blocks(int num_sms);
 

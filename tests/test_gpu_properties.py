@@ -1,0 +1,145 @@
+"""GPU tests of the step-kernel variants and of size-independent properties of the moments.
+
+* the bulk-copy (TMA) staged kernel `cheb_step_bulk` (kernels_bulk.cu) against the general kernel `cheb_step`
+  on the same inputs, every dtype and ELL width, both x-staging modes and several pipeline depths, and against the
+  CPU oracle (moment tolerance of north_star: 1e-5 for f32/c64, 1e-11 for f64/c128, relative to max |mu|);
+* properties that hold at any size (used at benchmark-like sizes where the oracle would take too long):
+  mu_0 = N / 2 exactly for the +-1 / unit-modulus stochastic starters, invariance under the batch size, the row
+  order (locality tile) and the rank count, run-to-run bit reproducibility.
+
+Engine tuning knobs are read from the environment when a context is created (engine.cu), so each variant is a
+fresh `pb.kpm` object created under a patched environment.
+"""
+import os
+from contextlib import contextmanager
+
+import numpy as np
+import pytest
+
+import pybinding_b200 as pb
+from oracle.oracle import OracleKPM
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.complex64): 1e-5,
+       np.dtype(np.float64): 1e-11, np.dtype(np.complex128): 1e-11}
+KNOBS = ("PBK_BULK", "PBK_XS", "PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL")
+
+
+@contextmanager
+def knobs(**kw):
+    saved = {k: os.environ.get(k) for k in KNOBS}
+    for k in KNOBS:
+        os.environ.pop(k, None)
+    os.environ.update({k: str(v) for k, v in kw.items()})
+    try:
+        yield
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+
+
+def rel_err(actual, expected):
+    actual, expected = np.asarray(actual), np.asarray(expected)
+    return float(np.abs(actual - expected).max() / np.abs(expected).max())
+
+
+def dos_moments(model, energy_range, M, R, max_batch=0, **kw):
+    with knobs(**kw):
+        kpm = pb.kpm(model, energy_range=energy_range, silent=True, max_batch=max_batch)
+        mom = kpm.impl.moments_dos(M, R)
+        return mom, kpm.stats
+
+
+def model_for(dtype, k):
+    dtype = np.dtype(dtype)
+    if k == 7:
+        if dtype.kind == "c":
+            pytest.skip("the cubic generator is real")
+        return pb.cubic_anderson(14, disorder=2.0, dtype=dtype), (-8.2, 8.2)   # 2744 sites, 6 neighbours + onsite
+    field = 400.0 if dtype.kind == "c" else 0.0
+    onsite = 0.3 if k == 4 else 0.0
+    return pb.graphene_rectangle(9.0, onsite=onsite, dtype=dtype, magnetic_field=field), (-9, 9)
+
+
+@pytest.mark.parametrize("k", [3, 4, 7])
+@pytest.mark.parametrize("dtype", [np.float32, np.complex64, np.float64, np.complex128], ids=lambda d: np.dtype(d).name)
+def test_bulk_kernel_matches_general_kernel_and_oracle(dtype, k):
+    dtype = np.dtype(dtype)
+    model, er = model_for(dtype, k)
+    M, R = 66, 12
+    general, s0 = dos_moments(model, er, M, R, PBK_BULK=0)
+    assert s0.bulk_launches == 0 and s0.step_launches == M // 2
+    expected = OracleKPM(model.hamiltonian, energy_range=er, hp=True).dos_moments(M, R)
+    assert rel_err(general, expected) < TOL[dtype]
+    for kw in (dict(), dict(PBK_XS=0), dict(PBK_BULK=2), dict(PBK_BULK=7, PBK_XS=0), dict(PBK_BULK=3, PBK_TILE=64)):
+        staged, s1 = dos_moments(model, er, M, R, **kw)
+        assert s1.bulk_launches == M // 2 - 1, "the staged kernel did not run: {}".format(kw)  # all but the r1 = H r0 / 2 step
+        assert rel_err(staged, expected) < TOL[dtype]
+        assert rel_err(staged, general) < 1e-12   # same arithmetic, same summation tree
+
+
+@pytest.mark.parametrize("R", [1, 2, 5, 8, 33, 64])
+def test_bulk_kernel_lane_counts(R):
+    """Every chunks-per-row geometry: R = 1 falls back to the scalar general kernel, the others are staged"""
+    model = pb.graphene_rectangle(12.0, dtype=np.complex64, magnetic_field=300.0)
+    M = 34
+    general, _ = dos_moments(model, (-9, 9), M, R, PBK_BULK=0)
+    staged, s = dos_moments(model, (-9, 9), M, R)
+    assert rel_err(staged, general) < 1e-12
+    assert (s.bulk_launches > 0) == (R > 1)
+
+
+def test_mu0_is_half_the_system_size():
+    """mu_0 = <r|r> / 2 = N / 2 exactly for +-1 and for exp(i phi) starters, at any size"""
+    for dtype, field in ((np.float32, 0.0), (np.complex64, 50.0)):
+        model = pb.graphene_rectangle(120.0, dtype=dtype, magnetic_field=field)   # 0.55 M sites
+        n = model.hamiltonian.shape[0]
+        mom, s = dos_moments(model, (-8.5, 8.5), 18, 8)
+        assert s.bulk_launches > 0
+        assert abs(mom[0].real - n / 2) <= (0 if dtype == np.float32 else 2e-7 * n)
+        assert abs(mom[0].imag) == 0
+        # mu_1 = <r|H~|r>: purely real for a Hermitian H; |mu_n| <= N/2 * 2
+        assert np.abs(mom.imag).max() <= 1e-6 * n
+        assert np.abs(mom).max() <= n
+
+
+def test_invariance_under_batching_order_and_reproducibility():
+    model = pb.graphene_rectangle(60.0, dtype=np.complex64, magnetic_field=100.0)   # 137 k sites
+    M, R = 130, 16
+    base, s = dos_moments(model, (-8.5, 8.5), M, R)
+    assert s.batch == 16 and s.bulk_launches > 0
+    again, _ = dos_moments(model, (-8.5, 8.5), M, R)
+    assert np.array_equal(base, again), "moments must be bit-reproducible run to run"
+    scale = np.abs(base).max()
+    for kw, mb in ((dict(), 4), (dict(), 6), (dict(PBK_TILE=-1), 0), (dict(PBK_TILE=1024), 0), (dict(PBK_MT_SEQUENTIAL=1), 0),
+                   (dict(PBK_BULK=0, PBK_TILE=64), 0)):
+        other, _ = dos_moments(model, (-8.5, 8.5), M, R, max_batch=mb, **kw)
+        assert np.abs(other - base).max() / scale < 2e-6, (kw, mb)   # f32 vectors: only the summation order differs
+
+
+def test_f64_invariance_is_tight():
+    model = pb.graphene_rectangle(40.0, dtype=np.float64, onsite=0.2)
+    M, R = 98, 6
+    base, _ = dos_moments(model, (-9, 9), M, R)
+    scale = np.abs(base).max()
+    for kw, mb in ((dict(), 2), (dict(PBK_TILE=-1), 0), (dict(PBK_BULK=0), 0), (dict(PBK_XS=0, PBK_BULK=6), 3)):
+        other, _ = dos_moments(model, (-9, 9), M, R, max_batch=mb, **kw)
+        assert np.abs(other - base).max() / scale < 1e-12, (kw, mb)
+
+
+def test_ldos_equals_dos_of_unit_vectors_and_sum_rule():
+    """sum over all sites of the LDOS moments = trace moments: mu_n^{DOS-exact} = sum_i mu_n^{(i)} (small system)"""
+    model = pb.graphene_rectangle(3.0, dtype=np.float64, onsite=0.1)
+    n = model.hamiltonian.shape[0]
+    kpm = pb.kpm(model, energy_range=(-9, 9), silent=True)
+    M = 34
+    ldos = kpm.impl.moments_ldos(M, list(range(n)))          # M x n
+    h = model.hamiltonian.toarray().astype(np.float64)
+    a, b = kpm.scaling_factors
+    w = np.linalg.eigvalsh(h)
+    t = np.cos(np.arange(M)[:, None] * np.arccos((w - b) / a)[None, :]).sum(axis=1)   # trace of T_n(H~)
+    t[0] *= 0.5
+    assert np.abs(ldos.sum(axis=1).real - t).max() / np.abs(t).max() < 1e-11
