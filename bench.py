@@ -237,7 +237,7 @@ def main():
     for _ in range(args.warmup):
         moments = kpm.impl.moments_dos(M, R)
     sampler = ClockSampler(local_rank)
-    step_times, wall_times, launches, step_ms, step_bytes, step_launches, starter_ms = [], [], 0, 0.0, 0.0, 0, 0.0
+    step_times, wall_times, launches, step_ms, step_bytes, step_launches, starter_ms, bulk_launches = [], [], 0, 0.0, 0.0, 0, 0.0, 0
     barrier()
     sampler.start()
     for _ in range(args.steps):
@@ -253,6 +253,7 @@ def main():
         step_ms += s.step_ms
         step_bytes += s.step_bytes
         step_launches += s.step_launches
+        bulk_launches += s.bulk_launches
         starter_ms += s.starter_ms
         batch = s.batch
     clocks = sampler.stop()
@@ -263,7 +264,9 @@ def main():
     achieved = (step_bytes / step_launches) / (step_ms / step_launches * 1e-3) / 1e9 if step_launches else 0.0
     s_item = np.dtype(w["dtype"]).itemsize
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                    traffic=ncu_traffic(args.workload), peak_source=peak_src, kernel="cheb_step (fused SpMM + moments)",
+                    traffic=ncu_traffic(args.workload), peak_source=peak_src,
+                    kernel="cheb_step_bulk (fused SpMM + moments, operands staged by cp.async.bulk)" if bulk_launches
+                    else "cheb_step (fused SpMM + moments)", staged_launches=int(bulk_launches),
                     algorithmic_bytes_per_launch=step_bytes / max(step_launches, 1),
                     launch_ms=step_ms / max(step_launches, 1), vectors_per_pass=batch,
                     bytes_model="rows*[k*(s+4) + 3*R*s], s={}".format(s_item))

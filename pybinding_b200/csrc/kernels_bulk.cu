@@ -211,18 +211,30 @@ __global__ void pack_ell_kernel(const T* __restrict__ val, const int32_t* __rest
 
 using BulkKernel = void (*)(BulkDev);
 
-int resident_bulk_blocks(BulkKernel fn, int block, int dyn_smem) {
+constexpr int BULK_MAX_DYN = 200 * 1024;
+
+/// resident CTAs per SM for (kernel, dynamic shared memory); the opt-in shared-memory limit of a kernel is raised
+/// once, to the largest size the launcher ever asks for
+cudaError_t resident_bulk_blocks(BulkKernel fn, int block, int dyn_smem, int* out) {
     static std::mutex mutex;
     static std::map<std::tuple<BulkKernel, int, int>, int> cache;
+    static std::map<BulkKernel, bool> raised;
     std::lock_guard<std::mutex> lock(mutex);
+    if (!raised[fn]) {
+        cudaError_t const err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_MAX_DYN);
+        if (err != cudaSuccess) return err;
+        raised[fn] = true;
+    }
     auto const key = std::make_tuple(fn, block, dyn_smem);
     auto const it = cache.find(key);
-    if (it != cache.end()) return it->second;
-    if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
+    if (it != cache.end()) { *out = it->second; return cudaSuccess; }
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, block, dyn_smem) != cudaSuccess || nb < 1) nb = 1;
+    cudaError_t const err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, block, dyn_smem);
+    if (err != cudaSuccess) return err;
+    if (nb < 1) return cudaErrorLaunchOutOfResources;
     cache[key] = nb;
-    return nb;
+    *out = nb;
+    return cudaSuccess;
 }
 
 constexpr int BULK_TPB = 256;
@@ -260,9 +272,12 @@ cudaError_t launch_bulk_t(StepArgs const& a, int num_sms, cudaStream_t stream, L
     uint32_t const hoff = BULK_TPB * 16u * (a.bulk_xstage ? 2u : 1u);
     uint32_t const stage_bytes = hoff + (static_cast<uint32_t>(rpb) * rec + 127u) / 128u * 128u;
     int const dyn = static_cast<int>(stages * stage_bytes + 16u * stages);
-    if (dyn > 200 * 1024) return cudaSuccess;
+    if (dyn > BULK_MAX_DYN) return cudaSuccess;
     int64_t const need = (a.nrows + tile_rows - 1) / tile_rows;
-    int const cap = num_sms * (a.blocks_per_sm > 0 ? a.blocks_per_sm : resident_bulk_blocks(fn, BULK_TPB, dyn));
+    int resident = 0;
+    cudaError_t const occ = resident_bulk_blocks(fn, BULK_TPB, dyn, &resident);
+    if (occ != cudaSuccess) return occ;
+    int const cap = num_sms * (a.blocks_per_sm > 0 && a.blocks_per_sm < resident ? a.blocks_per_sm : resident);
     int grid = static_cast<int>(need < static_cast<int64_t>(cap) ? need : cap);
     if (grid > max_step_blocks(num_sms)) grid = max_step_blocks(num_sms);
     // the chunk cursor may run one grid-stride past the end before the loop stops: keep it inside uint32
