@@ -1022,7 +1022,8 @@ void Engine::moments_kubo(int M, const float* left, const float* right, int num_
     upload_operator(vr, right, h);
     int const s = dtype_size(dtype);
     size_t const vbytes = static_cast<size_t>(n) * s;
-    size_t const stack_bytes = vbytes * M;
+    size_t const row_pitch = (vbytes + 127) / 128 * 128;   // stack rows start on 128-byte boundaries (16-byte cp.async in K4)
+    size_t const stack_bytes = row_pitch * M;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     if (2.0 * stack_bytes + 4.0 * vbytes > 0.9 * static_cast<double>(free_b)) {
@@ -1039,7 +1040,7 @@ void Engine::moments_kubo(int M, const float* left, const float* right, int num_
     shard(num_random, &first, &count);
     seed_stream(first);
     stats.batch = 1;
-    auto row_of = [&](DevBuf& st, int k) { return static_cast<void*>(st.as<char>() + static_cast<size_t>(k) * vbytes); };
+    auto row_of = [&](DevBuf& st, int k) { return static_cast<void*>(st.as<char>() + static_cast<size_t>(k) * row_pitch); };
     for (int j = 0; j < count; ++j) {
         generate_random_block(h, 1, 1, u.as());
         PBK_CUDA(cudaEventRecord(ev2, stream));
@@ -1062,7 +1063,7 @@ void Engine::moments_kubo(int M, const float* left, const float* right, int num_
         }
         PBK_CUDA(cudaEventRecord(ev3, stream));
         double flops = 0;
-        PBK_CUDA(launch_kubo_gemm(dtype, lstack.as(), rstack.as(), M, n, mu.as<double>(), num_sms, stream, &flops));
+        PBK_CUDA(launch_kubo_gemm(dtype, lstack.as(), rstack.as(), M, n, static_cast<int64_t>(row_pitch), mu.as<double>(), num_sms, stream, &flops));
         launches += dtype_complex(dtype) ? 4 : 2;
         PBK_CUDA(cudaEventRecord(ev1, stream));
         PBK_CUDA(cudaEventSynchronize(ev1));

@@ -103,9 +103,10 @@ cudaError_t launch_random_transform(int dtype, const uint32_t* raw, int64_t n, i
                                     void* dst, cudaStream_t s);
 
 // ---- Kubo-Bastin contraction (kubo.cu) -------------------------------------------------------
-/// C (M x M, c128 row-major) += A (M x N) * B^H (N x M); A, B row-major stacks of the Hamiltonian's scalar type
-cudaError_t launch_kubo_gemm(int dtype, const void* A, const void* B, int M, int64_t N, double* C_c128, int num_sms,
-                             cudaStream_t s, double* flops);
+/// C (M x M, c128 row-major) += A (M x N) * B^H (N x M); A, B row-major stacks of the Hamiltonian's scalar type,
+/// rows `pitch_bytes` apart (a multiple of 16; base pointers 16-byte aligned)
+cudaError_t launch_kubo_gemm(int dtype, const void* A, const void* B, int M, int64_t N, int64_t pitch_bytes, double* C_c128,
+                             int num_sms, cudaStream_t s, double* flops);
 
 // ---- Lanczos helpers (bounds) ----------------------------------------------------------------
 /// v0 = t - b_prev*v0 - a*v1 (a read from a_dev[0]) ; out[0] = |v0|^2

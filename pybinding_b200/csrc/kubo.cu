@@ -2,88 +2,161 @@
 //
 // Replaces MomentMultiplication::matrix_mul_add (cppcore/src/kpm/Moments.cpp:92-101,123-126), which
 // the reference evaluates as a single-threaded Eigen GEMM on two host-resident M x N stacks.
-// This is the one dense, tensor-core-shaped piece of the KPM path.  tcgen05/UMMA has no fp64 kind,
-// so the fp64 tensor pipe is driven with mma.sync.m8n8k4.f64 (DMMA); f32/c64 stacks are widened to
-// fp64 while staging into shared memory, so every scalar type accumulates in double.
+// This is the one dense, tensor-core-shaped piece of the KPM path.  tcgen05/UMMA has no fp64 kind, so the
+// fp64 tensor pipe is driven with mma.sync f64 -- on sm_100a every f64 shape compiles to DMMA.8x8x4, measured
+// peak 37.1 TFLOP/s (tools/probe/dmma_probe.cu, profiles/r01_fp64_mma_probe.jsonl).  f32/c64 stacks are widened
+// to fp64 when the fragments are read from shared memory, so every scalar type accumulates in double.
 //
 // Both stacks are K-major (each moment row is contiguous over the N sites), i.e. the "TN" case where
 // A and B fragments use the same access pattern.  Complex stacks are treated as real M x 2N matrices:
 //   Re(mu) = A' * B'^T                      with A' = [.. ar_k, ai_k ..], B' = [.. br_k, bi_k ..]
-//   Im(mu) = A'' * B'^T                     with A'' = [.. ai_k, -ar_k ..]   (pair swap + negate on load)
+//   Im(mu) = A'' * B'^T                     with A'' = [.. ai_k, -ar_k ..]   (pair swap + negate on fragment load)
+//
+// Kernel: 128 x 128 tile per CTA (8 warps, 32 x 64 per warp = 32 DMMAs per k4-step out of 12 fragment loads),
+// operands streamed global -> shared by a 3-stage cp.async ring of 128-byte rows (16 doubles / 32 floats per
+// stage, zero-filled past the edges), padded row stride so that fragment loads are bank-conflict free.
+// M is rarely a multiple of the tile (the reference's num_moments is 4k+2): 8 x 8 blocks that lie entirely
+// outside the matrix are skipped, so the cost follows ceil(M/8)^2 blocks, not the padded tile area.
 // Split-K over N with per-split partial tiles and a fixed-order reduction keeps the result deterministic.
 #include "kernels.cuh"
+
+#include <type_traits>
 
 namespace pbk {
 
 namespace {
 
-constexpr int TM = 64, TN = 64, TK = 32, PAD = 4;
-constexpr int GEMM_THREADS = 128;
+constexpr int BM = 128, BN = 128;       // CTA tile
+constexpr int GEMM_THREADS = 256;       // 8 warps: 4 (m) x 2 (n), warp tile 32 x 64
+constexpr int ROW_BYTES = 128;          // bytes of one operand row per pipeline stage
+constexpr int GEMM_STAGES = 3;
+
+template<class Real> struct Geom {
+    static constexpr int TKE = ROW_BYTES / sizeof(Real);          // k-extent of a stage in elements
+    static constexpr int PAD = sizeof(Real) == 8 ? 32 : 16;       // bytes: stride = 20 doubles / 36 floats
+    static constexpr int STRIDE = ROW_BYTES + PAD;                // bytes between rows in shared memory
+    static constexpr int TILE = BM * STRIDE;                      // one operand, one stage
+    static constexpr int STAGE = 2 * TILE;
+    static constexpr int SMEM = GEMM_STAGES * STAGE;
+};
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {  // zero-fills past src_bytes
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ double lds_as_double(uint32_t addr, double) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ double lds_as_double(uint32_t addr, float) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return static_cast<double>(v); }
 
-/// part[z][Mp][Mp] = A[:, kz] * B[:, kz]^T  over the K-range of split z.  `ld` = row stride in real elements.
+/// part[z][Mp][Mp] = A[:, kz] * B[:, kz]^T  over the K-range of split z.  `ld` = row stride in real elements
+/// (a multiple of 16 bytes); kchunk is a multiple of the stage extent.
 template<class Real, bool IMAG>
-__global__ void __launch_bounds__(GEMM_THREADS) kubo_gemm_kernel(const Real* __restrict__ A, const Real* __restrict__ B, int M, int64_t K,
-                                                                 int64_t ld, double* __restrict__ part, int Mp, int64_t kchunk) {
-    __shared__ double As[TM][TK + PAD];
-    __shared__ double Bs[TN][TK + PAD];
+__global__ void __launch_bounds__(GEMM_THREADS, 1) kubo_gemm_kernel(const Real* __restrict__ A, const Real* __restrict__ B, int M, int64_t K,
+                                                                    int64_t ld, double* __restrict__ part, int Mp, int64_t kchunk) {
+    using G = Geom<Real>;
+    constexpr int TKE = G::TKE;
+    constexpr int EPC = 16 / sizeof(Real);   // elements per 16-byte chunk
+    extern __shared__ __align__(128) unsigned char gemm_smem[];
+    uint32_t const smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(gemm_smem));
+
     int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int const wm = warp >> 1, wn = warp & 1;
-    int const m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    int const m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     int64_t const kbeg = static_cast<int64_t>(blockIdx.z) * kchunk;
     int64_t const kend = (kbeg + kchunk < K) ? kbeg + kchunk : K;
+    int const nstage = static_cast<int>((kend - kbeg + TKE - 1) / TKE);
 
-    double c[4][4][2];
+    // 8 x 8 blocks of this warp that intersect the matrix (warp-uniform)
+    int mi_cnt = (M - (m0 + wm * 32) + 7) / 8; mi_cnt = mi_cnt < 0 ? 0 : (mi_cnt > 4 ? 4 : mi_cnt);
+    int nj_cnt = (M - (n0 + wn * 64) + 7) / 8; nj_cnt = nj_cnt < 0 ? 0 : (nj_cnt > 8 ? 8 : nj_cnt);
+
+    // ---- producer side: each thread moves 4 chunks of A and 4 of B per stage ----
+    int const lrow = tid >> 3, lch = tid & 7;            // rows lrow + 32 i, 16-byte chunk lch of the 128-byte row
+    auto load_stage = [&](int st, int slot) {
+        int64_t const k0 = kbeg + static_cast<int64_t>(st) * TKE + lch * EPC;
+        int64_t const left = (kend - k0) * static_cast<int64_t>(sizeof(Real));
+        uint32_t const kbytes = left <= 0 ? 0u : (left >= 16 ? 16u : static_cast<uint32_t>(left));
+        uint32_t const dst0 = smem0 + slot * G::STAGE + lrow * G::STRIDE + lch * 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int const r = lrow + 32 * i;
+            bool const okA = (m0 + r < M) && kbytes > 0, okB = (n0 + r < M) && kbytes > 0;
+            const Real* const srcA = okA ? A + static_cast<int64_t>(m0 + r) * ld + k0 : A;
+            const Real* const srcB = okB ? B + static_cast<int64_t>(n0 + r) * ld + k0 : B;
+            cp_async16(dst0 + i * 32 * G::STRIDE, srcA, okA ? kbytes : 0u);
+            cp_async16(dst0 + G::TILE + i * 32 * G::STRIDE, srcB, okB ? kbytes : 0u);
+        }
+    };
+
+    double c[4][8][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
+        for (int j = 0; j < 8; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
 
-    for (int64_t k0 = kbeg; k0 < kend; k0 += TK) {
-#pragma unroll 4
-        for (int i = tid; i < TM * TK; i += GEMM_THREADS) {
-            int const r = i / TK, cc = i % TK;
-            int64_t const kk = k0 + cc;
-            double va = 0.0, vb = 0.0;
-            if (kk < kend) {
-                if (m0 + r < M) {
-                    if (IMAG) { double const t = static_cast<double>(A[static_cast<int64_t>(m0 + r) * ld + (kk ^ 1)]); va = (kk & 1) ? -t : t; }
-                    else va = static_cast<double>(A[static_cast<int64_t>(m0 + r) * ld + kk]);
-                }
-                if (n0 + r < M) vb = static_cast<double>(B[static_cast<int64_t>(n0 + r) * ld + kk]);
-            }
-            As[r][cc] = va;
-            Bs[r][cc] = vb;
-        }
-        __syncthreads();
 #pragma unroll
-        for (int kk = 0; kk < TK; kk += 4) {
-            double a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[wm * 32 + i * 8 + (lane >> 2)][kk + (lane & 3)];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[wn * 32 + j * 8 + (lane >> 2)][kk + (lane & 3)];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma_m8n8k4(c[i][j][0], c[i][j][1], a[i], b[j]);
-        }
-        __syncthreads();
+    for (int st = 0; st < GEMM_STAGES - 1; ++st) {
+        if (st < nstage) load_stage(st, st);
+        cp_async_commit();
     }
+
+    // fragment addresses: thread holds A[row = lane / 4][k = lane % 4] of each 8 x 4 block (B alike)
+    int const fr = lane >> 2, fk = lane & 3;
+    int const fkA = IMAG ? (fk ^ 1) : fk;                     // A'' = [ai, -ar]: neighbour element, sign by parity
+    double const sgnA = (IMAG && (fk & 1)) ? -1.0 : 1.0;
+    uint32_t const offA = (wm * 32 + fr) * G::STRIDE + fkA * sizeof(Real);
+    uint32_t const offB = G::TILE + (wn * 64 + fr) * G::STRIDE + fk * sizeof(Real);
+
+    // main loop, instantiated twice: interior tiles run the branch-free version, tiles on the matrix edge skip the
+    // 8 x 8 blocks that lie outside (both conditions are CTA-uniform)
+    auto mainloop = [&](auto edge_tag) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
+        int slot = 0;
+        for (int st = 0; st < nstage; ++st) {
+            cp_async_wait<GEMM_STAGES - 2>();   // stage st has landed (for this thread's copies)
+            __syncthreads();                    // ... for everyone's; and everyone is done with the slot refilled below
+            {
+                int const nxt = st + GEMM_STAGES - 1;
+                int nslot = slot + GEMM_STAGES - 1; if (nslot >= GEMM_STAGES) nslot -= GEMM_STAGES;
+                if (nxt < nstage) load_stage(nxt, nslot);
+                cp_async_commit();
+            }
+            uint32_t const base = smem0 + slot * G::STAGE;
+#pragma unroll
+            for (int kk = 0; kk < TKE; kk += 4) {
+                double a[4], b[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = sgnA * lds_as_double(base + offA + i * 8 * G::STRIDE + kk * sizeof(Real), Real{});
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b[j] = lds_as_double(base + offB + j * 8 * G::STRIDE + kk * sizeof(Real), Real{});
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (!EDGE || i < mi_cnt) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (!EDGE || j < nj_cnt) dmma_m8n8k4(c[i][j][0], c[i][j][1], a[i], b[j]);
+                    }
+                }
+            }
+            if (++slot == GEMM_STAGES) slot = 0;
+        }
+    };
+    if (m0 + BM <= M && n0 + BN <= M) mainloop(std::false_type{});
+    else mainloop(std::true_type{});
+    cp_async_wait<0>();
 
     double* out = part + static_cast<int64_t>(blockIdx.z) * Mp * Mp;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
             int const row = m0 + wm * 32 + i * 8 + (lane >> 2);
-            int const col = n0 + wn * 32 + j * 8 + (lane & 3) * 2;
-            out[static_cast<int64_t>(row) * Mp + col] = c[i][j][0];
-            out[static_cast<int64_t>(row) * Mp + col + 1] = c[i][j][1];
+            int const col = n0 + wn * 64 + j * 8 + (lane & 3) * 2;
+            *reinterpret_cast<double2*>(out + static_cast<int64_t>(row) * Mp + col) = make_double2(c[i][j][0], c[i][j][1]);
         }
 }
 
@@ -97,27 +170,43 @@ __global__ void kubo_reduce_kernel(const double* part, int ksplit, int Mp, int M
 }
 
 template<class Real>
-cudaError_t gemm_t(const void* A, const void* B, int M, int64_t N, bool cplx, double* C, int num_sms, cudaStream_t s, double* flops) {
-    int const tiles = (M + TM - 1) / TM;
-    int const Mp = tiles * TM;
+cudaError_t gemm_t(const void* A, const void* B, int M, int64_t N, int64_t pitch_bytes, bool cplx, double* C, int num_sms, cudaStream_t s,
+                   double* flops) {
+    using G = Geom<Real>;
+    if (pitch_bytes % 16 != 0 || reinterpret_cast<uintptr_t>(A) % 16 != 0 || reinterpret_cast<uintptr_t>(B) % 16 != 0) return cudaErrorInvalidValue;
+    int const tiles = (M + BM - 1) / BM;
+    int const Mp = tiles * BM;
     int64_t const K = cplx ? 2 * N : N;
-    int ksplit = (2 * num_sms + tiles * tiles - 1) / (tiles * tiles);
+    int64_t const ld = pitch_bytes / static_cast<int64_t>(sizeof(Real));
+    // split-K: about four waves of CTAs so that the light edge tiles do not leave SMs idle at the end
+    int ksplit = (4 * num_sms + tiles * tiles - 1) / (tiles * tiles);
+    int64_t const max_split = (K + 8 * G::TKE - 1) / (8 * G::TKE);   // at least 8 stages per CTA
+    if (ksplit > max_split) ksplit = static_cast<int>(max_split);
+    if (ksplit > 128) ksplit = 128;
     if (ksplit < 1) ksplit = 1;
-    if (ksplit > 64) ksplit = 64;
     int64_t kchunk = (K + ksplit - 1) / ksplit;
-    kchunk = (kchunk + TK - 1) / TK * TK;
+    kchunk = (kchunk + G::TKE - 1) / G::TKE * G::TKE;
     ksplit = static_cast<int>((K + kchunk - 1) / kchunk);
 
+    static bool raised[2] = {false, false};
+    auto const k_re = kubo_gemm_kernel<Real, false>;
+    auto const k_im = kubo_gemm_kernel<Real, true>;
+    if (!raised[sizeof(Real) == 8]) {
+        cudaError_t e = cudaFuncSetAttribute(k_re, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_im, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        if (e != cudaSuccess) return e;
+        raised[sizeof(Real) == 8] = true;
+    }
     double* part = nullptr;
     cudaError_t err = cudaMallocAsync(&part, sizeof(double) * ksplit * Mp * Mp, s);
     if (err != cudaSuccess) return err;
     dim3 const grid(tiles, tiles, ksplit);
     auto const* a = static_cast<const Real*>(A);
     auto const* b = static_cast<const Real*>(B);
-    kubo_gemm_kernel<Real, false><<<grid, GEMM_THREADS, 0, s>>>(a, b, M, K, K, part, Mp, kchunk);
+    k_re<<<grid, GEMM_THREADS, G::SMEM, s>>>(a, b, M, K, ld, part, Mp, kchunk);
     kubo_reduce_kernel<<<(M * M + 255) / 256, 256, 0, s>>>(part, ksplit, Mp, M, C, 0);
     if (cplx) {
-        kubo_gemm_kernel<Real, true><<<grid, GEMM_THREADS, 0, s>>>(a, b, M, K, K, part, Mp, kchunk);
+        k_im<<<grid, GEMM_THREADS, G::SMEM, s>>>(a, b, M, K, ld, part, Mp, kchunk);
         kubo_reduce_kernel<<<(M * M + 255) / 256, 256, 0, s>>>(part, ksplit, Mp, M, C, 1);
     }
     err = cudaGetLastError();
@@ -176,13 +265,13 @@ cudaError_t launch_kubo_gamma_sum(const double* mu_c128, int M, const double* sc
     return cudaGetLastError();
 }
 
-cudaError_t launch_kubo_gemm(int dtype, const void* A, const void* B, int M, int64_t N, double* C_c128, int num_sms,
+cudaError_t launch_kubo_gemm(int dtype, const void* A, const void* B, int M, int64_t N, int64_t pitch_bytes, double* C_c128, int num_sms,
                              cudaStream_t s, double* flops) {
     switch (dtype) {
-        case F32: return gemm_t<float>(A, B, M, N, false, C_c128, num_sms, s, flops);
-        case C64: return gemm_t<float>(A, B, M, N, true, C_c128, num_sms, s, flops);
-        case F64: return gemm_t<double>(A, B, M, N, false, C_c128, num_sms, s, flops);
-        case C128: return gemm_t<double>(A, B, M, N, true, C_c128, num_sms, s, flops);
+        case F32: return gemm_t<float>(A, B, M, N, pitch_bytes, false, C_c128, num_sms, s, flops);
+        case C64: return gemm_t<float>(A, B, M, N, pitch_bytes, true, C_c128, num_sms, s, flops);
+        case F64: return gemm_t<double>(A, B, M, N, pitch_bytes, false, C_c128, num_sms, s, flops);
+        case C128: return gemm_t<double>(A, B, M, N, pitch_bytes, true, C_c128, num_sms, s, flops);
         default: return cudaErrorInvalidValue;
     }
 }
