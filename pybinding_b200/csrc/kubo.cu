@@ -20,6 +20,7 @@
 // Split-K over N with per-split partial tiles and a fixed-order reduction keeps the result deterministic.
 #include "kernels.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace pbk {
@@ -178,11 +179,13 @@ cudaError_t gemm_t(const void* A, const void* B, int M, int64_t N, int64_t pitch
     int const Mp = tiles * BM;
     int64_t const K = cplx ? 2 * N : N;
     int64_t const ld = pitch_bytes / static_cast<int64_t>(sizeof(Real));
-    // split-K: about four waves of CTAs so that the light edge tiles do not leave SMs idle at the end
-    int ksplit = (4 * num_sms + tiles * tiles - 1) / (tiles * tiles);
+    // split-K: many waves of CTAs (one CTA per SM) so that neither the light edge tiles nor the last wave leave
+    // SMs idle for long; each split costs one 128 x 128 partial tile of traffic, negligible next to its k-range
+    static int const waves = [] { char const* v = std::getenv("PBK_KUBO_WAVES"); int w = v ? std::atoi(v) : 16; return w < 1 ? 1 : w; }();
+    int ksplit = (waves * num_sms + tiles * tiles - 1) / (tiles * tiles);
     int64_t const max_split = (K + 8 * G::TKE - 1) / (8 * G::TKE);   // at least 8 stages per CTA
     if (ksplit > max_split) ksplit = static_cast<int>(max_split);
-    if (ksplit > 128) ksplit = 128;
+    if (ksplit > 512) ksplit = 512;
     if (ksplit < 1) ksplit = 1;
     int64_t kchunk = (K + ksplit - 1) / ksplit;
     kchunk = (kchunk + G::TKE - 1) / G::TKE * G::TKE;
