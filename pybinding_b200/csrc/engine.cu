@@ -174,6 +174,7 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
     h_data.assign(static_cast<const char*>(data), static_cast<const char*>(data) + nnz * dtype_size(dt));
     has_h = true;
     natural = DeviceHamiltonian();
+    bfs_ready = BfsOrder();
     optimized = DeviceHamiltonian();
     unscaled = DeviceHamiltonian();
     have_bounds = false;
@@ -327,6 +328,43 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
     }
 }
 
+/// BFS relabelling from src[0]; slice k = the k-th shell (OptimizedHamiltonian.cpp:88-143)
+BfsOrder Engine::bfs_order(Indices const& target) const {
+    BfsOrder b;
+    b.target = target;
+    auto& queue = b.queue;
+    queue.reserve(n);
+    queue.push_back(target.src[0]);
+    b.reorder_map.assign(n, -1);
+    b.reorder_map[target.src[0]] = 0;
+    std::vector<int32_t> borders{1};
+    for (int64_t h2_row = 0; h2_row < n; ++h2_row) {
+        if (h2_row >= static_cast<int64_t>(queue.size())) {
+            throw Error(PBK_RUNTIME_ERROR, "KPM: the Hamiltonian graph is not connected; the optimal_size "
+                                           "reordering needs a connected system");
+        }
+        int32_t const row = queue[h2_row];
+        for (int p = h_indptr[row]; p < h_indptr[row + 1]; ++p) {
+            int32_t const c = h_indices[p];
+            if (b.reorder_map[c] < 0) { b.reorder_map[c] = static_cast<int32_t>(queue.size()); queue.push_back(c); }
+        }
+        if (h2_row == borders.back() - 1) borders.push_back(static_cast<int32_t>(queue.size()));
+    }
+    borders.pop_back();
+    for (int32_t i : target.src) b.idx.src.push_back(b.reorder_map[i]);
+    for (int32_t i : target.dest) b.idx.dest.push_back(b.reorder_map[i]);
+    auto find_offset = [&](std::vector<int32_t> const& v) {
+        int32_t const mx = *std::max_element(v.begin(), v.end());
+        auto const it = std::find_if(borders.begin(), borders.end(), [&](int32_t bd) { return bd > mx; });
+        return static_cast<int>(it - borders.begin());
+    };
+    b.map.src_offset = find_offset(b.idx.src);
+    b.map.dest_offset = find_offset(b.idx.dest);
+    b.map.data = std::move(borders);
+    b.valid = true;
+    return b;
+}
+
 void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int order, Indices const& target) {
     require_hamiltonian();
     PBK_CUDA(cudaSetDevice(device));
@@ -344,35 +382,19 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
         dh.reordered = true;
         dh.tile = locality_tile;
     } else if (order == ORDER_BFS) {
-        // BFS relabelling from src[0]; slice k = the k-th shell (OptimizedHamiltonian.cpp:88-143)
-        queue.reserve(n);
-        queue.push_back(target.src[0]);
-        dh.reorder_map.assign(n, -1);
-        dh.reorder_map[target.src[0]] = 0;
-        std::vector<int32_t> borders{1};
-        for (int64_t h2_row = 0; h2_row < n; ++h2_row) {
-            if (h2_row >= static_cast<int64_t>(queue.size())) {
-                throw Error(PBK_RUNTIME_ERROR, "KPM: the Hamiltonian graph is not connected; the optimal_size "
-                                               "reordering needs a connected system");
-            }
-            int32_t const row = queue[h2_row];
-            for (int p = h_indptr[row]; p < h_indptr[row + 1]; ++p) {
-                int32_t const c = h_indices[p];
-                if (dh.reorder_map[c] < 0) { dh.reorder_map[c] = static_cast<int32_t>(queue.size()); queue.push_back(c); }
-            }
-            if (h2_row == borders.back() - 1) borders.push_back(static_cast<int32_t>(queue.size()));
+        if (bfs_ready.valid_for(target)) {  // moments_ldos already ran the relabelling to look at the slice map
+            queue = std::move(bfs_ready.queue);
+            dh.reorder_map = std::move(bfs_ready.reorder_map);
+            dh.idx = bfs_ready.idx;
+            dh.map = bfs_ready.map;
+            bfs_ready = BfsOrder();
+        } else {
+            BfsOrder b = bfs_order(target);
+            queue = std::move(b.queue);
+            dh.reorder_map = std::move(b.reorder_map);
+            dh.idx = b.idx;
+            dh.map = b.map;
         }
-        borders.pop_back();
-        for (int32_t i : target.src) dh.idx.src.push_back(dh.reorder_map[i]);
-        for (int32_t i : target.dest) dh.idx.dest.push_back(dh.reorder_map[i]);
-        auto find_offset = [&](std::vector<int32_t> const& v) {
-            int32_t const mx = *std::max_element(v.begin(), v.end());
-            auto const it = std::find_if(borders.begin(), borders.end(), [&](int32_t b) { return b > mx; });
-            return static_cast<int>(it - borders.begin());
-        };
-        dh.map.src_offset = find_offset(dh.idx.src);
-        dh.map.dest_offset = find_offset(dh.idx.dest);
-        dh.map.data = std::move(borders);
         dh.reordered = true;
         dh.sliced = true;
     } else {
@@ -929,7 +951,28 @@ void Engine::moments_ldos(int M, const int32_t* idx, int nidx, cd* out) {
     if (nidx < 1) throw Error(PBK_INVALID_ARGUMENT, "at least one index is required");
     for (int i = 0; i < nidx; ++i) if (idx[i] < 0 || idx[i] >= n) throw Error(PBK_INVALID_ARGUMENT, "LDOS index out of range");
     Indices target{std::vector<int32_t>(idx, idx + nidx), std::vector<int32_t>(idx, idx + nidx)};
-    auto& h = optimized_for(target);
+    // Light-cone slicing pays when the sources sit together (one site, the orbitals of a site, a small region).
+    // For sources spread over the sample the union of the light cones is the whole system from the first steps on:
+    // then the full-system locality layout with the staged kernel is the faster way to advance the unit vectors.
+    bool spread = false;
+    if (config.optimal_size && nidx > 1 && !(optimized.valid && optimized.original_idx == target)) {
+        if (!bfs_ready.valid_for(target)) bfs_ready = bfs_order(target);
+        double sliced_rows = 0;
+        for (int k = 0; k < M; ++k) sliced_rows += static_cast<double>(bfs_ready.map.optimal_size(k, M));
+        spread = sliced_rows > 0.6 * static_cast<double>(M) * static_cast<double>(n);
+        if (spread) bfs_ready = BfsOrder();
+    }
+    DeviceHamiltonian* hp = nullptr;
+    if (spread) {
+        auto& hn = natural_hamiltonian();
+        hn.idx = Indices{};
+        for (int32_t i : target.src) hn.idx.src.push_back(hn.reordered ? hn.reorder_map[i] : i);
+        hn.idx.dest = hn.idx.src;
+        hp = &hn;
+    } else {
+        hp = &optimized_for(target);
+    }
+    auto& h = *hp;
     bool const opt = config.optimal_size != 0 && h.sliced;
     reset_stats(M, h, opt, nidx);
     begin_moments();

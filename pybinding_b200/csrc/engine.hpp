@@ -87,6 +87,16 @@ struct DeviceHamiltonian {
     uint64_t memory() const { return static_cast<uint64_t>(ell.rows) * ell.k * 0 + val.bytes() + col.bytes(); }
 };
 
+/// Result of the breadth-first relabelling from a source (host side of OptimizedHamiltonian::create_reordered)
+struct BfsOrder {
+    bool valid = false;
+    Indices target, idx;               // requested (original) and relabelled indices
+    std::vector<int32_t> queue;        // new -> original
+    std::vector<int32_t> reorder_map;  // original -> new
+    SliceMap map;
+    bool valid_for(Indices const& t) const { return valid && target == t; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // NCCL through dlopen: no link-time dependency, single-GPU use never touches it
 // ------------------------------------------------------------------------------------------------
@@ -205,6 +215,8 @@ private:
     // ---- helpers ----
     void require_hamiltonian() const;
     void compute_bounds();
+    BfsOrder bfs_order(Indices const& target) const;
+    BfsOrder bfs_ready;           // relabelling computed ahead of build_device_hamiltonian (moments_ldos)
     void build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int order, Indices const& target);
     DeviceHamiltonian& natural_hamiltonian();
     DeviceHamiltonian& optimized_for(Indices const& target);

@@ -147,3 +147,29 @@ def test_ldos_equals_dos_of_unit_vectors_and_sum_rule():
     t = np.cos(np.arange(M)[:, None] * np.arccos((w - b) / a)[None, :]).sum(axis=1)   # trace of T_n(H~)
     t[0] *= 0.5
     assert np.abs(ldos.sum(axis=1).real - t).max() / np.abs(t).max() < 1e-11
+
+
+def test_spread_ldos_sites_use_full_system_layout_and_match_single_site_runs():
+    """LDOS at sites spread over the sample (core.ldos(indices), cppcore/src/kpm/Core.cpp:58-72): the union of the light
+    cones is the whole system, so the engine advances the unit vectors on the locality layout with the staged kernel;
+    each column must equal the light-cone-sliced single-site run."""
+    model = pb.graphene_rectangle(30.0, dtype=np.complex128, magnetic_field=200.0, disorder=0.3)
+    kpm = pb.kpm(model, energy_range=(-9.2, 9.2), silent=True)
+    fn = model.system.find_nearest
+    sites = [fn([x, y]) for x in (-12, -4, 4, 12) for y in (-10, 0, 10)]
+    M = 258
+    batch = kpm.impl.moments_ldos(M, sites)
+    s = kpm.stats
+    assert s.bulk_launches > 0 and s.opt_nnz == s.nnz          # full system, staged kernel
+    single = pb.kpm(model, energy_range=(-9.2, 9.2), silent=True)
+    for j, site in enumerate(sites):
+        one = single.impl.moments_ldos(M, [site])[:, 0]
+        assert np.abs(batch[:, j] - one).max() / np.abs(one).max() < 1e-11
+    assert single.stats.bulk_launches == 0 and single.stats.opt_nnz < single.stats.nnz   # light-cone sliced
+    # neighbouring sites (one cell) keep the sliced layout
+    near = [fn([0, 0], "A"), fn([0, 0], "B")]
+    both = single.impl.moments_ldos(M, near)
+    assert single.stats.opt_nnz < single.stats.nnz
+    for j, site in enumerate(near):
+        one = kpm.impl.moments_ldos(M, [site])[:, 0]
+        assert np.abs(both[:, j] - one).max() / np.abs(one).max() < 1e-11
