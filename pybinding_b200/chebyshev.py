@@ -466,8 +466,11 @@ def kpm(model, energy_range=None, kernel="default", num_threads="auto", silent=F
         Don't show any progress messages.
     **kwargs
         `matrix_format`, `optimal_size`, `interleaved`, `lanczos_precision`, `progress_callback` as in the
-        reference (cppmodule/src/kpm.cpp:27-36), plus `device` (CUDA ordinal) and `max_batch`.
+        reference (cppmodule/src/kpm.cpp:27-36), plus `device` (CUDA ordinal), `max_batch` and
+        `binding`: "ctypes" (default; `_CudaImpl` over the C ABI) or "pybind11" (the compiled `_pbkpm` module, the
+        C++ counterpart of `_pybinding.kpm`, csrc/pymodule.cpp).  Both drive the same `libpbkpm.so`.
     """
+    binding = kwargs.pop("binding", "ctypes")
     if kernel != "default":
         kwargs["kernel"] = kernel
     if num_threads != "auto":
@@ -476,6 +479,11 @@ def kpm(model, energy_range=None, kernel="default", num_threads="auto", silent=F
         kwargs["progress_callback"] = _ComputeProgressReporter()
     if silent:
         del kwargs["progress_callback"]
+    if binding == "pybind11":
+        from . import _pbkpm   # ImportError if the extension was not built: there is no fallback
+        return KPM(_pbkpm.kpm(model, tuple(energy_range) if energy_range is not None else (0, 0), **kwargs))
+    if binding != "ctypes":
+        raise ValueError("binding must be 'ctypes' or 'pybind11'")
     return KPM(_CudaImpl(model, energy_range or (0, 0), **kwargs))
 
 

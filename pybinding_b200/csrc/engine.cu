@@ -1075,6 +1075,7 @@ void Engine::moments_kubo(int M, const float* left, const float* right, int num_
     begin_moments();
     progress(-1, num_random);
     DevBuf lstack(stack_bytes), rstack(stack_bytes), u(vbytes), mu(sizeof(cd) * static_cast<size_t>(M) * M);
+    DevBuf gemm_ws(kubo_gemm_workspace_bytes(dtype, M, n, num_sms));
     vec_a.ensure(vbytes);
     vec_b.ensure(vbytes);
     ensure_moment_buffers(1, M);
@@ -1106,7 +1107,8 @@ void Engine::moments_kubo(int M, const float* left, const float* right, int num_
         }
         PBK_CUDA(cudaEventRecord(ev3, stream));
         double flops = 0;
-        PBK_CUDA(launch_kubo_gemm(dtype, lstack.as(), rstack.as(), M, n, static_cast<int64_t>(row_pitch), mu.as<double>(), num_sms, stream, &flops));
+        PBK_CUDA(launch_kubo_gemm(dtype, lstack.as(), rstack.as(), M, n, static_cast<int64_t>(row_pitch), mu.as<double>(),
+                                  gemm_ws.as<double>(), gemm_ws.bytes(), num_sms, stream, &flops));
         launches += dtype_complex(dtype) ? 4 : 2;
         PBK_CUDA(cudaEventRecord(ev1, stream));
         PBK_CUDA(cudaEventSynchronize(ev1));
@@ -1179,7 +1181,7 @@ void Engine::calc_dos(const double* energy, int ne, double broadening, int num_r
     moments_dos(M, num_random, m.data());
     auto const g = damping_coefficients(config.kernel, config.lambda_value, M);
     for (int i = 0; i < M; ++i) m[i] *= g[i];
-    reconstruct_spectral_density(m.data(), M, 1, 0, 1, energy, ne, s, out);
+    spectral_density_device(m.data(), M, 1, 0, 1, energy, ne, s, out);
     last_total_seconds = now_seconds() - t0;
 }
 
@@ -1191,7 +1193,7 @@ void Engine::calc_ldos(const double* energy, int ne, double broadening, const in
     moments_ldos(M, idx, nidx, m.data());
     auto const g = damping_coefficients(config.kernel, config.lambda_value, M);
     for (int k = 0; k < M; ++k) for (int i = 0; i < nidx; ++i) m[static_cast<size_t>(k) * nidx + i] *= g[k];
-    reconstruct_spectral_density(m.data(), M, nidx, 1, nidx, energy, ne, s, out);
+    spectral_density_device(m.data(), M, nidx, 1, nidx, energy, ne, s, out);
     last_total_seconds = now_seconds() - t0;
 }
 
@@ -1202,10 +1204,8 @@ void Engine::calc_greens(int row, const int32_t* cols, int ncols, const double* 
     std::vector<cd> m(static_cast<size_t>(M) * ncols);
     moments_greens(M, row, cols, ncols, m.data());
     auto const g = damping_coefficients(config.kernel, config.lambda_value, M);
-    for (int i = 0; i < ncols; ++i) {
-        for (int k = 0; k < M; ++k) m[static_cast<size_t>(i) * M + k] *= g[k];
-        reconstruct_greens(m.data() + static_cast<size_t>(i) * M, M, energy, ne, s, out + static_cast<size_t>(i) * ne);
-    }
+    for (int i = 0; i < ncols; ++i) for (int k = 0; k < M; ++k) m[static_cast<size_t>(i) * M + k] *= g[k];
+    greens_device(m.data(), M, ncols, energy, ne, s, out);
     last_total_seconds = now_seconds() - t0;
 }
 
@@ -1235,6 +1235,39 @@ void Engine::calc_conductivity(const float* left, const float* right, const doub
     PBK_CUDA(cudaStreamSynchronize(stream));
     reconstruct_kubo_bastin(sum_nm.data(), samples, mu, nmu, temperature, s, out);
     last_total_seconds = now_seconds() - t0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reconstruction on the device (reconstruct.cu): damped moments go up, curves come back
+// ------------------------------------------------------------------------------------------------
+void Engine::spectral_density_device(const cd* moments, int M, int cols, int64_t col_stride, int64_t n_stride, const double* energy, int ne,
+                                     Scale s, double* out) {
+    if (ne <= 0) return;
+    PBK_CUDA(cudaSetDevice(device));
+    size_t const count = static_cast<size_t>(M) * std::max<int64_t>(n_stride, 1);
+    std::vector<double> scaled(ne);
+    for (int i = 0; i < ne; ++i) scaled[i] = (energy[i] - s.b) / s.a;
+    DevBuf mu_dev(sizeof(cd) * count), e_dev(sizeof(double) * ne), out_dev(sizeof(double) * static_cast<size_t>(ne) * cols);
+    PBK_CUDA(cudaMemcpyAsync(mu_dev.as(), moments, sizeof(cd) * count, cudaMemcpyHostToDevice, stream));
+    PBK_CUDA(cudaMemcpyAsync(e_dev.as(), scaled.data(), sizeof(double) * ne, cudaMemcpyHostToDevice, stream));
+    double const k = static_cast<double>(2 / pi_f) / s.a;  // real_t{2 / constant::pi}
+    PBK_CUDA(launch_spectral_density(mu_dev.as<double>(), M, cols, col_stride, n_stride, e_dev.as<double>(), ne, k, out_dev.as<double>(), stream));
+    PBK_CUDA(cudaMemcpyAsync(out, out_dev.as(), sizeof(double) * static_cast<size_t>(ne) * cols, cudaMemcpyDeviceToHost, stream));
+    PBK_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Engine::greens_device(const cd* moments, int M, int cols, const double* energy, int ne, Scale s, cd* out) {
+    if (ne <= 0) return;
+    PBK_CUDA(cudaSetDevice(device));
+    std::vector<double> scaled(ne);
+    for (int i = 0; i < ne; ++i) scaled[i] = (energy[i] - s.b) / s.a;
+    size_t const count = static_cast<size_t>(M) * cols;
+    DevBuf mu_dev(sizeof(cd) * count), e_dev(sizeof(double) * ne), out_dev(sizeof(cd) * static_cast<size_t>(ne) * cols);
+    PBK_CUDA(cudaMemcpyAsync(mu_dev.as(), moments, sizeof(cd) * count, cudaMemcpyHostToDevice, stream));
+    PBK_CUDA(cudaMemcpyAsync(e_dev.as(), scaled.data(), sizeof(double) * ne, cudaMemcpyHostToDevice, stream));
+    PBK_CUDA(launch_greens(mu_dev.as<double>(), M, cols, e_dev.as<double>(), ne, 1.0 / s.a, out_dev.as<double>(), stream));
+    PBK_CUDA(cudaMemcpyAsync(out, out_dev.as(), sizeof(cd) * static_cast<size_t>(ne) * cols, cudaMemcpyDeviceToHost, stream));
+    PBK_CUDA(cudaStreamSynchronize(stream));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1280,34 +1313,9 @@ std::string Engine::report(bool shortform) const {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Reconstruction (kpm/reconstruct.hpp), double precision; the reference's float constants are kept
+// Kubo-Bastin: Fermi-weighted integration over the energy samples (kpm/reconstruct.hpp:133-143); the O(points * M^2)
+// Gamma-matrix sum runs on the device (kubo.cu).  Double precision; the reference's float constants are kept
 // ------------------------------------------------------------------------------------------------
-void reconstruct_spectral_density(const cd* moments, int M, int cols, int64_t col_stride, int64_t n_stride,
-                                  const double* energy, int ne, Scale s, double* out) {
-    double const k = static_cast<double>(2 / pi_f) / s.a;  // real_t{2 / constant::pi}
-    for (int c = 0; c < cols; ++c) {
-        for (int i = 0; i < ne; ++i) {
-            double const E = (energy[i] - s.b) / s.a;
-            double const ac = std::acos(E);
-            double sum = 0;
-            for (int q = 0; q < M; ++q) sum += moments[q * n_stride + c * col_stride].real() * std::cos(q * ac);
-            out[static_cast<size_t>(c) * ne + i] = k / std::sqrt(1 - E * E) * sum;
-        }
-    }
-}
-
-void reconstruct_greens(const cd* moments, int M, const double* energy, int ne, Scale s, cd* out) {
-    cd const i1(0, 1);
-    cd const k = -2.0 * i1 / s.a;
-    for (int i = 0; i < ne; ++i) {
-        double const E = (energy[i] - s.b) / s.a;
-        double const ac = std::acos(E);
-        cd sum(0, 0);
-        for (int q = 0; q < M; ++q) sum += moments[q] * std::exp(-i1 * (q * ac));
-        out[i] = k / std::sqrt(1 - E * E) * sum;
-    }
-}
-
 void reconstruct_kubo_bastin(const double* sum_nm, const std::vector<double>& en, const double* mu, int nmu,
                              double temperature, Scale s, cd* out) {
     int const np = static_cast<int>(en.size());

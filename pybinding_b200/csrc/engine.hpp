@@ -241,6 +241,10 @@ private:
     void generate_random_block(DeviceHamiltonian const& h, int lanes, int R, void* dst);
     void seed_stream(int64_t skip_vectors);
 
+    void spectral_density_device(const cd* moments, int M, int cols, int64_t col_stride, int64_t n_stride, const double* energy, int ne,
+                                 Scale s, double* out);
+    void greens_device(const cd* moments, int M, int cols, const double* energy, int ne, Scale s, cd* out);
+
     void shard(int total, int* first, int* count) const;
     void allreduce(double* dev, int64_t count);
 
@@ -261,9 +265,6 @@ std::vector<double> damping_coefficients(int kernel, double lambda_value, int n)
 int kernel_required_num_moments(int kernel, double lambda_value, double scaled_broadening);
 
 // reconstruction (include/kpm/reconstruct.hpp:16-143), double precision with the reference's float constants
-void reconstruct_spectral_density(const cd* moments, int M, int cols, int64_t col_stride, int64_t n_stride,
-                                  const double* energy, int ne, Scale s, double* out);
-void reconstruct_greens(const cd* moments, int M, const double* energy, int ne, Scale s, cd* out);
 void reconstruct_kubo_bastin(const double* sum_nm_c128, const std::vector<double>& scaled_samples, const double* mu, int nmu,
                              double temperature, Scale s, cd* out);
 cudaError_t launch_kubo_gamma_sum(const double* mu_c128, int M, const double* scaled_samples, int np, double* out_c128, cudaStream_t s);

@@ -104,9 +104,19 @@ cudaError_t launch_random_transform(int dtype, const uint32_t* raw, int64_t n, i
 
 // ---- Kubo-Bastin contraction (kubo.cu) -------------------------------------------------------
 /// C (M x M, c128 row-major) += A (M x N) * B^H (N x M); A, B row-major stacks of the Hamiltonian's scalar type,
-/// rows `pitch_bytes` apart (a multiple of 16; base pointers 16-byte aligned)
+/// rows `pitch_bytes` apart (a multiple of 16; base pointers 16-byte aligned).  `workspace` holds the split-K partial
+/// tiles (kubo_gemm_workspace_bytes).
+size_t kubo_gemm_workspace_bytes(int dtype, int M, int64_t N, int num_sms);
 cudaError_t launch_kubo_gemm(int dtype, const void* A, const void* B, int M, int64_t N, int64_t pitch_bytes, double* C_c128,
-                             int num_sms, cudaStream_t s, double* flops);
+                             double* workspace, size_t workspace_bytes, int num_sms, cudaStream_t s, double* flops);
+
+// ---- reconstruction (reconstruct.cu) ----------------------------------------------------------
+/// out[c * ne + i] = k / sqrt(1 - E_i^2) * sum_q Re(mu[q * n_stride + c * col_stride]) cos(q acos E_i); E already scaled
+cudaError_t launch_spectral_density(const double* mu_c128, int M, int cols, int64_t col_stride, int64_t n_stride, const double* scaled_energy,
+                                    int ne, double k, double* out, cudaStream_t s);
+/// out[c * ne + i] = -2i / (a sqrt(1 - E_i^2)) * sum_q mu[c * M + q] exp(-i q acos E_i); out is c128
+cudaError_t launch_greens(const double* mu_c128, int M, int cols, const double* scaled_energy, int ne, double inv_a, double* out_c128,
+                          cudaStream_t s);
 
 // ---- Lanczos helpers (bounds) ----------------------------------------------------------------
 /// v0 = t - b_prev*v0 - a*v1 (a read from a_dev[0]) ; out[0] = |v0|^2

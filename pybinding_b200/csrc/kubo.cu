@@ -28,7 +28,7 @@ namespace pbk {
 namespace {
 
 constexpr int BM = 128, BN = 128;       // CTA tile
-constexpr int GEMM_THREADS = 256;       // 8 warps: 4 (m) x 2 (n), warp tile 32 x 64
+// warps: 4 (m) x WN (n); WN = 2: 8 warps with 32 x 64 warp tiles, WN = 4: 16 warps with 32 x 32 warp tiles
 constexpr int ROW_BYTES = 128;          // bytes of one operand row per pipeline stage
 constexpr int GEMM_STAGES = 3;
 
@@ -55,8 +55,8 @@ __device__ __forceinline__ double lds_as_double(uint32_t addr, float) { float v;
 
 /// part[z][Mp][Mp] = A[:, kz] * B[:, kz]^T  over the K-range of split z.  `ld` = row stride in real elements
 /// (a multiple of 16 bytes); kchunk is a multiple of the stage extent.
-template<class Real, bool IMAG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) kubo_gemm_kernel(const Real* __restrict__ A, const Real* __restrict__ B, int M, int64_t K,
+template<class Real, bool IMAG, int WN>
+__global__ void __launch_bounds__(128 * WN, 1) kubo_gemm_kernel(const Real* __restrict__ A, const Real* __restrict__ B, int M, int64_t K,
                                                                     int64_t ld, double* __restrict__ part, int Mp, int64_t kchunk) {
     using G = Geom<Real>;
     constexpr int TKE = G::TKE;
@@ -64,8 +64,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) kubo_gemm_kernel(const Real* 
     extern __shared__ __align__(128) unsigned char gemm_smem[];
     uint32_t const smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(gemm_smem));
 
+    constexpr int GEMM_THREADS = 128 * WN;
+    constexpr int NB = BN / WN / 8;          // 8-column blocks per warp: 8 (WN = 2) or 4 (WN = 4)
+    constexpr int WCOLS = BN / WN;
+    constexpr int LOADS = 1024 / GEMM_THREADS;  // 16-byte chunks per thread, per operand, per stage
     int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int const wm = warp >> 1, wn = warp & 1;
+    int const wm = warp / WN, wn = warp % WN;
     int const m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     int64_t const kbeg = static_cast<int64_t>(blockIdx.z) * kchunk;
     int64_t const kend = (kbeg + kchunk < K) ? kbeg + kchunk : K;
@@ -73,31 +77,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) kubo_gemm_kernel(const Real* 
 
     // 8 x 8 blocks of this warp that intersect the matrix (warp-uniform)
     int mi_cnt = (M - (m0 + wm * 32) + 7) / 8; mi_cnt = mi_cnt < 0 ? 0 : (mi_cnt > 4 ? 4 : mi_cnt);
-    int nj_cnt = (M - (n0 + wn * 64) + 7) / 8; nj_cnt = nj_cnt < 0 ? 0 : (nj_cnt > 8 ? 8 : nj_cnt);
+    int nj_cnt = (M - (n0 + wn * WCOLS) + 7) / 8; nj_cnt = nj_cnt < 0 ? 0 : (nj_cnt > NB ? NB : nj_cnt);
 
-    // ---- producer side: each thread moves 4 chunks of A and 4 of B per stage ----
-    int const lrow = tid >> 3, lch = tid & 7;            // rows lrow + 32 i, 16-byte chunk lch of the 128-byte row
+    // ---- producer side: each thread moves LOADS chunks of A and of B per stage ----
+    constexpr int RSTEP = GEMM_THREADS / 8;
+    int const lrow = tid >> 3, lch = tid & 7;            // rows lrow + RSTEP i, 16-byte chunk lch of the 128-byte row
     auto load_stage = [&](int st, int slot) {
         int64_t const k0 = kbeg + static_cast<int64_t>(st) * TKE + lch * EPC;
         int64_t const left = (kend - k0) * static_cast<int64_t>(sizeof(Real));
         uint32_t const kbytes = left <= 0 ? 0u : (left >= 16 ? 16u : static_cast<uint32_t>(left));
         uint32_t const dst0 = smem0 + slot * G::STAGE + lrow * G::STRIDE + lch * 16;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int const r = lrow + 32 * i;
+        for (int i = 0; i < LOADS; ++i) {
+            int const r = lrow + RSTEP * i;
             bool const okA = (m0 + r < M) && kbytes > 0, okB = (n0 + r < M) && kbytes > 0;
             const Real* const srcA = okA ? A + static_cast<int64_t>(m0 + r) * ld + k0 : A;
             const Real* const srcB = okB ? B + static_cast<int64_t>(n0 + r) * ld + k0 : B;
-            cp_async16(dst0 + i * 32 * G::STRIDE, srcA, okA ? kbytes : 0u);
-            cp_async16(dst0 + G::TILE + i * 32 * G::STRIDE, srcB, okB ? kbytes : 0u);
+            cp_async16(dst0 + i * RSTEP * G::STRIDE, srcA, okA ? kbytes : 0u);
+            cp_async16(dst0 + G::TILE + i * RSTEP * G::STRIDE, srcB, okB ? kbytes : 0u);
         }
     };
 
-    double c[4][8][2];
+    double c[4][NB][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
+        for (int j = 0; j < NB; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
 
 #pragma unroll
     for (int st = 0; st < GEMM_STAGES - 1; ++st) {
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) kubo_gemm_kernel(const Real* 
     int const fkA = IMAG ? (fk ^ 1) : fk;                     // A'' = [ai, -ar]: neighbour element, sign by parity
     double const sgnA = (IMAG && (fk & 1)) ? -1.0 : 1.0;
     uint32_t const offA = (wm * 32 + fr) * G::STRIDE + fkA * sizeof(Real);
-    uint32_t const offB = G::TILE + (wn * 64 + fr) * G::STRIDE + fk * sizeof(Real);
+    uint32_t const offB = G::TILE + (wn * WCOLS + fr) * G::STRIDE + fk * sizeof(Real);
 
     // main loop, instantiated twice: interior tiles run the branch-free version, tiles on the matrix edge skip the
     // 8 x 8 blocks that lie outside (both conditions are CTA-uniform)
@@ -129,16 +134,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) kubo_gemm_kernel(const Real* 
             uint32_t const base = smem0 + slot * G::STAGE;
 #pragma unroll
             for (int kk = 0; kk < TKE; kk += 4) {
-                double a[4], b[8];
+                double a[4], b[NB];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) a[i] = sgnA * lds_as_double(base + offA + i * 8 * G::STRIDE + kk * sizeof(Real), Real{});
 #pragma unroll
-                for (int j = 0; j < 8; ++j) b[j] = lds_as_double(base + offB + j * 8 * G::STRIDE + kk * sizeof(Real), Real{});
+                for (int j = 0; j < NB; ++j) b[j] = lds_as_double(base + offB + j * 8 * G::STRIDE + kk * sizeof(Real), Real{});
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (!EDGE || i < mi_cnt) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
+                        for (int j = 0; j < NB; ++j)
                             if (!EDGE || j < nj_cnt) dmma_m8n8k4(c[i][j][0], c[i][j][1], a[i], b[j]);
                     }
                 }
@@ -154,9 +159,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) kubo_gemm_kernel(const Real* 
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < NB; ++j) {
             int const row = m0 + wm * 32 + i * 8 + (lane >> 2);
-            int const col = n0 + wn * 64 + j * 8 + (lane & 3) * 2;
+            int const col = n0 + wn * WCOLS + j * 8 + (lane & 3) * 2;
             *reinterpret_cast<double2*>(out + static_cast<int64_t>(row) * Mp + col) = make_double2(c[i][j][0], c[i][j][1]);
         }
 }
@@ -171,49 +176,63 @@ __global__ void kubo_reduce_kernel(const double* part, int ksplit, int Mp, int M
 }
 
 template<class Real>
-cudaError_t gemm_t(const void* A, const void* B, int M, int64_t N, int64_t pitch_bytes, bool cplx, double* C, int num_sms, cudaStream_t s,
-                   double* flops) {
+void gemm_plan(int M, int64_t N, bool cplx, int num_sms, int* Mp, int64_t* K, int* ksplit, int64_t* kchunk) {
     using G = Geom<Real>;
-    if (pitch_bytes % 16 != 0 || reinterpret_cast<uintptr_t>(A) % 16 != 0 || reinterpret_cast<uintptr_t>(B) % 16 != 0) return cudaErrorInvalidValue;
     int const tiles = (M + BM - 1) / BM;
-    int const Mp = tiles * BM;
-    int64_t const K = cplx ? 2 * N : N;
-    int64_t const ld = pitch_bytes / static_cast<int64_t>(sizeof(Real));
-    // split-K: many waves of CTAs (one CTA per SM) so that neither the light edge tiles nor the last wave leave
+    *Mp = tiles * BM;
+    *K = cplx ? 2 * N : N;
+    // split-K: a few waves of CTAs (one CTA per SM) so that neither the light edge tiles nor the last wave leave
     // SMs idle for long; each split costs one 128 x 128 partial tile of traffic, negligible next to its k-range
-    static int const waves = [] { char const* v = std::getenv("PBK_KUBO_WAVES"); int w = v ? std::atoi(v) : 16; return w < 1 ? 1 : w; }();
-    int ksplit = (waves * num_sms + tiles * tiles - 1) / (tiles * tiles);
-    int64_t const max_split = (K + 8 * G::TKE - 1) / (8 * G::TKE);   // at least 8 stages per CTA
-    if (ksplit > max_split) ksplit = static_cast<int>(max_split);
-    if (ksplit > 512) ksplit = 512;
-    if (ksplit < 1) ksplit = 1;
-    int64_t kchunk = (K + ksplit - 1) / ksplit;
-    kchunk = (kchunk + G::TKE - 1) / G::TKE * G::TKE;
-    ksplit = static_cast<int>((K + kchunk - 1) / kchunk);
+    static int const waves = [] { char const* v = std::getenv("PBK_KUBO_WAVES"); int w = v ? std::atoi(v) : 8; return w < 1 ? 1 : w; }();
+    int ks = (waves * num_sms + tiles * tiles - 1) / (tiles * tiles);
+    int64_t const max_split = (*K + 8 * G::TKE - 1) / (8 * G::TKE);   // at least 8 stages per CTA
+    if (ks > max_split) ks = static_cast<int>(max_split);
+    if (ks > 512) ks = 512;
+    if (ks < 1) ks = 1;
+    int64_t kc = (*K + ks - 1) / ks;
+    kc = (kc + G::TKE - 1) / G::TKE * G::TKE;
+    *ksplit = static_cast<int>((*K + kc - 1) / kc);
+    *kchunk = kc;
+}
 
-    static bool raised[2] = {false, false};
-    auto const k_re = kubo_gemm_kernel<Real, false>;
-    auto const k_im = kubo_gemm_kernel<Real, true>;
-    if (!raised[sizeof(Real) == 8]) {
+template<class Real, int WN>
+cudaError_t gemm_launch(const Real* a, const Real* b, int M, int64_t K, int64_t ld, bool cplx, double* C, double* part, int Mp, int ksplit,
+                        int64_t kchunk, cudaStream_t s) {
+    using G = Geom<Real>;
+    static bool raised = false;
+    auto const k_re = kubo_gemm_kernel<Real, false, WN>;
+    auto const k_im = kubo_gemm_kernel<Real, true, WN>;
+    if (!raised) {
         cudaError_t e = cudaFuncSetAttribute(k_re, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_im, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
         if (e != cudaSuccess) return e;
-        raised[sizeof(Real) == 8] = true;
+        raised = true;
     }
-    double* part = nullptr;
-    cudaError_t err = cudaMallocAsync(&part, sizeof(double) * ksplit * Mp * Mp, s);
-    if (err != cudaSuccess) return err;
+    int const tiles = Mp / BM;
     dim3 const grid(tiles, tiles, ksplit);
-    auto const* a = static_cast<const Real*>(A);
-    auto const* b = static_cast<const Real*>(B);
-    k_re<<<grid, GEMM_THREADS, G::SMEM, s>>>(a, b, M, K, ld, part, Mp, kchunk);
+    k_re<<<grid, 128 * WN, G::SMEM, s>>>(a, b, M, K, ld, part, Mp, kchunk);
     kubo_reduce_kernel<<<(M * M + 255) / 256, 256, 0, s>>>(part, ksplit, Mp, M, C, 0);
     if (cplx) {
-        k_im<<<grid, GEMM_THREADS, G::SMEM, s>>>(a, b, M, K, ld, part, Mp, kchunk);
+        k_im<<<grid, 128 * WN, G::SMEM, s>>>(a, b, M, K, ld, part, Mp, kchunk);
         kubo_reduce_kernel<<<(M * M + 255) / 256, 256, 0, s>>>(part, ksplit, Mp, M, C, 1);
     }
-    err = cudaGetLastError();
-    cudaFreeAsync(part, s);
+    return cudaGetLastError();
+}
+
+template<class Real>
+cudaError_t gemm_t(const void* A, const void* B, int M, int64_t N, int64_t pitch_bytes, bool cplx, double* C, double* workspace,
+                   size_t workspace_bytes, int num_sms, cudaStream_t s, double* flops) {
+    if (pitch_bytes % 16 != 0 || reinterpret_cast<uintptr_t>(A) % 16 != 0 || reinterpret_cast<uintptr_t>(B) % 16 != 0) return cudaErrorInvalidValue;
+    int Mp = 0, ksplit = 0;
+    int64_t K = 0, kchunk = 0;
+    gemm_plan<Real>(M, N, cplx, num_sms, &Mp, &K, &ksplit, &kchunk);
+    if (workspace_bytes < sizeof(double) * static_cast<size_t>(ksplit) * Mp * Mp) return cudaErrorInvalidValue;
+    int64_t const ld = pitch_bytes / static_cast<int64_t>(sizeof(Real));
+    static int const warps_n = [] { char const* v = std::getenv("PBK_KUBO_WN"); return (v && std::atoi(v) == 2) ? 2 : 4; }();
+    auto const* a = static_cast<const Real*>(A);
+    auto const* b = static_cast<const Real*>(B);
+    cudaError_t const err = warps_n == 2 ? gemm_launch<Real, 2>(a, b, M, K, ld, cplx, C, workspace, Mp, ksplit, kchunk, s)
+                                         : gemm_launch<Real, 4>(a, b, M, K, ld, cplx, C, workspace, Mp, ksplit, kchunk, s);
     if (flops) *flops = 2.0 * M * M * static_cast<double>(K) * (cplx ? 2 : 1);
     return err;
 }
@@ -268,13 +287,22 @@ cudaError_t launch_kubo_gamma_sum(const double* mu_c128, int M, const double* sc
     return cudaGetLastError();
 }
 
-cudaError_t launch_kubo_gemm(int dtype, const void* A, const void* B, int M, int64_t N, int64_t pitch_bytes, double* C_c128, int num_sms,
-                             cudaStream_t s, double* flops) {
+size_t kubo_gemm_workspace_bytes(int dtype, int M, int64_t N, int num_sms) {
+    int Mp = 0, ksplit = 0;
+    int64_t K = 0, kchunk = 0;
+    bool const cplx = dtype_complex(dtype);
+    if (dtype == F32 || dtype == C64) gemm_plan<float>(M, N, cplx, num_sms, &Mp, &K, &ksplit, &kchunk);
+    else gemm_plan<double>(M, N, cplx, num_sms, &Mp, &K, &ksplit, &kchunk);
+    return sizeof(double) * static_cast<size_t>(ksplit) * Mp * Mp;
+}
+
+cudaError_t launch_kubo_gemm(int dtype, const void* A, const void* B, int M, int64_t N, int64_t pitch_bytes, double* C_c128,
+                             double* workspace, size_t workspace_bytes, int num_sms, cudaStream_t s, double* flops) {
     switch (dtype) {
-        case F32: return gemm_t<float>(A, B, M, N, pitch_bytes, false, C_c128, num_sms, s, flops);
-        case C64: return gemm_t<float>(A, B, M, N, pitch_bytes, true, C_c128, num_sms, s, flops);
-        case F64: return gemm_t<double>(A, B, M, N, pitch_bytes, false, C_c128, num_sms, s, flops);
-        case C128: return gemm_t<double>(A, B, M, N, pitch_bytes, true, C_c128, num_sms, s, flops);
+        case F32: return gemm_t<float>(A, B, M, N, pitch_bytes, false, C_c128, workspace, workspace_bytes, num_sms, s, flops);
+        case C64: return gemm_t<float>(A, B, M, N, pitch_bytes, true, C_c128, workspace, workspace_bytes, num_sms, s, flops);
+        case F64: return gemm_t<double>(A, B, M, N, pitch_bytes, false, C_c128, workspace, workspace_bytes, num_sms, s, flops);
+        case C128: return gemm_t<double>(A, B, M, N, pitch_bytes, true, C_c128, workspace, workspace_bytes, num_sms, s, flops);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -59,3 +59,28 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower() or f == "_never_", os.path.join(dirpath, f)
+
+
+def test_pybind11_module_mirrors_the_reference_binding():
+    """`_pbkpm` (csrc/pymodule.cpp) is the compiled counterpart of `_pybinding.kpm` / `KPM` (cppmodule/src/kpm.cpp:8-102)"""
+    from pybinding_b200 import _pbkpm
+    assert _pbkpm.abi_version == _lib.load().pbk_version()
+    for name in ("kpm", "kpm_cuda", "KPM", "KPMKernel", "KPMStats", "DeferredXd", "jackson_kernel", "lorentz_kernel", "dirichlet_kernel"):
+        assert hasattr(_pbkpm, name), name
+    for name in ("moments", "calc_greens", "calc_dos", "calc_conductivity", "calc_ldos", "calc_spatial_ldos", "deferred_ldos",
+                 "report", "model", "system", "scaling_factors", "kernel", "stats"):     # cppmodule/src/kpm.cpp:76-102
+        assert hasattr(_pbkpm.KPM, name), name
+    # kernels are context-free: same numbers as the ctypes layer
+    assert np.array_equal(_pbkpm.jackson_kernel().damping_coefficients(12), pb.jackson_kernel().damping_coefficients(12))
+    assert _pbkpm.lorentz_kernel(3.0).required_num_moments(0.01) == pb.lorentz_kernel(3.0).required_num_moments(0.01)
+    with pytest.raises(ValueError):
+        _pbkpm.lorentz_kernel(0.0)
+    import ctypes as C
+    count = C.c_int(0)
+    _lib.load().pbk_device_count(C.byref(count))
+    if count.value == 0:   # std::runtime_error -> RuntimeError, like the reference's exceptions through pybind11
+        with pytest.raises(RuntimeError) as excinfo:
+            pb.kpm(pb.graphene_rectangle(2), silent=True, binding="pybind11")
+        assert "no CPU fallback" in str(excinfo.value)
+    with pytest.raises(ValueError):
+        pb.kpm(pb.graphene_rectangle(2), silent=True, binding="nope")

@@ -260,3 +260,50 @@ def test_api_contract():
     assert "moments" in kp.report() and "eps" in kp.report(True)
     sl = kpm.calc_spatial_ldos(energy, 0.3, pb.Rectangle(1.0))
     assert sl.data.shape == (25, len(sl.structure)) and len(sl.structure) > 10
+
+
+def test_pybind11_binding_equals_ctypes_binding():
+    """Both bindings drive the same C ABI: identical numbers, reference exception types, GIL released during the calls"""
+    model = pb.graphene_rectangle(10, onsite=0.2, magnetic_field=300.0)
+    energy = np.linspace(-2, 2, 41)
+    a = pb.kpm(model, energy_range=(-9, 9), silent=True)
+    calls = []
+    b = pb.kpm(model, energy_range=[-9, 9], binding="pybind11", kernel=pb.jackson_kernel(),
+               progress_callback=lambda delta, total: calls.append((delta, total)))
+    assert a.scaling_factors == b.scaling_factors
+    assert np.array_equal(a.calc_dos(energy, 0.2, num_random=3).data, b.calc_dos(energy, 0.2, num_random=3).data)
+    assert calls[0] == (-1, 3) and calls[-1] == (3, 3)
+    assert np.array_equal(a.calc_ldos(energy, 0.2, [0, 0]).data, b.calc_ldos(energy, 0.2, [0, 0]).data)
+    assert np.array_equal(a.calc_ldos(energy, 0.2, [1, 1], "B", reduce=False).data, b.calc_ldos(energy, 0.2, [1, 1], "B", reduce=False).data)
+    n = model.system.num_sites
+    assert np.array_equal(a.calc_greens(n // 2, n // 3, energy, 0.2), b.calc_greens(n // 2, n // 3, energy, 0.2))
+    ga, gb = a.calc_greens(5, [7, 9], energy, 0.2), b.calc_greens(5, [7, 9], energy, 0.2)
+    assert len(gb) == 2 and all(np.array_equal(x, y) for x, y in zip(ga, gb))
+    mu = np.linspace(-1, 1, 7)
+    sa = a.calc_conductivity(mu, 0.8, 300, "xy", num_random=1, num_points=100)
+    sb = b.calc_conductivity(mu, 0.8, 300, "xy", num_random=1, num_points=100)
+    assert np.array_equal(sa.data, sb.data)
+    alpha = np.zeros(model.hamiltonian.shape[0], np.complex128)
+    alpha[3] = 1
+    assert np.array_equal(a.moments(21, alpha), b.moments(21, alpha))
+    assert np.array_equal(a.moments(21, alpha, alpha[::-1].copy(), model.hamiltonian),
+                          b.moments(21, alpha, alpha[::-1].copy(), model.hamiltonian))
+    sl_a = a.calc_spatial_ldos(energy, 0.3, pb.Rectangle(1.0))
+    sl_b = b.calc_spatial_ldos(energy, 0.3, pb.Rectangle(1.0))
+    assert np.array_equal(sl_a.data, sl_b.data)
+    d = b.deferred_ldos(energy, 0.2, [0, 0])
+    assert np.array_equal(np.asarray(d.result).squeeze(), a.calc_ldos(energy, 0.2, [0, 0]).data) and d.solver is b.impl
+    assert "moments" in b.report() and b.stats.num_moments > 0 and b.stats.eps > 0
+    assert b.kernel.required_num_moments(0.01) == a.kernel.required_num_moments(0.01)
+    with pytest.raises(RuntimeError) as excinfo:
+        b.moments(10, [1, 2, 3])
+    assert "Size mismatch" in str(excinfo.value)
+    with pytest.raises(RuntimeError):
+        b.calc_greens(-1, 0, [0.0], 0.1)
+    with pytest.raises(RuntimeError):
+        b.calc_conductivity([0.0], 0.5, 0, direction="xw")
+    with pytest.raises(ValueError):
+        pb.kpm(model, energy_range=(3, -3), silent=True, binding="pybind11")
+    b.model = pb.graphene_rectangle(8)     # cpb::KPM::set_model: new Hamiltonian, same object
+    assert b.system.num_sites == pb.graphene_rectangle(8).system.num_sites
+    assert np.array_equal(b.calc_dos(energy, 0.3, 2).data, pb.kpm(pb.graphene_rectangle(8), energy_range=(-9, 9), silent=True).calc_dos(energy, 0.3, 2).data)
