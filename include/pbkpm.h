@@ -100,6 +100,7 @@ typedef struct pbk_stats {
     double moments_device_ms; /* device time of the whole moments phase (CUDA events on the library stream, from the
                                  first starter kernel to the moment copy-out, allreduce included) */
     int64_t bulk_launches;    /* step launches that ran the bulk-copy (TMA) staged kernel variant */
+    int64_t pair_launches;    /* launches of the two-step kernel (each advances the recursion by two steps = four moments) */
 } pbk_stats;
 
 /* Progress protocol of DefaultCompute (cppcore/src/kpm/default/Compute.cpp:133-145):

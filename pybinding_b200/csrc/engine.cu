@@ -144,6 +144,10 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     step_prefetch_mask = static_cast<int>(env_int("PBK_PFMASK", 0));
     bulk_stages = static_cast<int>(env_int("PBK_BULK", 4));
     bulk_xstage = env_int("PBK_XS", 1) != 0;
+    pair_mode = static_cast<int>(env_int("PBK_PAIR", 0));
+    pair_stages = static_cast<int>(env_int("PBK_PAIR_STAGES", 4));
+    pair_minb = static_cast<int>(env_int("PBK_PAIR_MINB", 0));
+    pair_max_r = static_cast<int>(env_int("PBK_PAIR_R", 0));
     PBK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (cudaEvent_t* e : {&ev0, &ev1, &ev2, &ev3, &ev_begin, &ev_end}) PBK_CUDA(cudaEventCreate(e));
     counter.alloc(64);
@@ -365,6 +369,64 @@ BfsOrder Engine::bfs_order(Indices const& target) const {
     return b;
 }
 
+/// Two-step kernel metadata (kernels_pair.cu): for every tile of `locality_tile` consecutive rows the sorted list of
+/// rows outside the tile that its rows reference (the one-ring halo), and the phase-2 column codes
+/// (>= 0: a row of the tile itself, < 0: -(1 + position in the halo list)), packed with the values like the ELL records.
+void Engine::build_pair_metadata(DeviceHamiltonian& dh, const int32_t* col, int64_t pitch, int k) {
+    int64_t const tile = dh.tile;
+    int64_t const ntiles = (n + tile - 1) / tile;
+    std::vector<int32_t> hptr(ntiles + 1, 0);
+    auto halo_of = [&](int64_t t, std::vector<int32_t>& buf) {
+        int64_t const r0 = t * tile, r1 = std::min<int64_t>(n, r0 + tile);
+        buf.clear();
+        for (int sidx = 0; sidx < k; ++sidx) {
+            const int32_t* cs = col + sidx * pitch;
+            for (int64_t r = r0; r < r1; ++r) { int32_t const c = cs[r]; if (c < r0 || c >= r1) buf.push_back(c); }
+        }
+        std::sort(buf.begin(), buf.end());
+        buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
+    };
+    parallel_rows(ntiles, [&](int64_t b, int64_t e) {
+        std::vector<int32_t> buf;
+        for (int64_t t = b; t < e; ++t) { halo_of(t, buf); hptr[t + 1] = static_cast<int32_t>(buf.size()); }
+    });
+    int hmax = 0;
+    for (int64_t t = 0; t < ntiles; ++t) { hmax = std::max(hmax, hptr[t + 1]); hptr[t + 1] += hptr[t]; }
+    std::vector<int32_t> hrows(std::max<int64_t>(hptr[ntiles], 1));
+    std::vector<int32_t> code(static_cast<size_t>(k) * pitch, 0);
+    parallel_rows(ntiles, [&](int64_t b, int64_t e) {
+        std::vector<int32_t> buf;
+        for (int64_t t = b; t < e; ++t) {
+            halo_of(t, buf);
+            std::copy(buf.begin(), buf.end(), hrows.begin() + hptr[t]);
+            int64_t const r0 = t * tile, r1 = std::min<int64_t>(n, r0 + tile);
+            for (int sidx = 0; sidx < k; ++sidx) {
+                const int32_t* cs = col + sidx * pitch;
+                int32_t* out = code.data() + sidx * pitch;
+                for (int64_t r = r0; r < r1; ++r) {
+                    int32_t const c = cs[r];
+                    if (c >= r0 && c < r1) { out[r] = c; }
+                    else { out[r] = -1 - static_cast<int32_t>(std::lower_bound(buf.begin(), buf.end(), c) - buf.begin()); }
+                }
+            }
+        }
+    });
+    dh.halo_max = hmax;
+    dh.halo_frac = static_cast<double>(hptr[ntiles]) / static_cast<double>(n);
+    dh.halo_ptr.alloc(sizeof(int32_t) * hptr.size());
+    dh.halo_rows.alloc(sizeof(int32_t) * hrows.size());
+    DevBuf code_dev(sizeof(int32_t) * code.size());
+    PBK_CUDA(cudaMemcpyAsync(dh.halo_ptr.as(), hptr.data(), sizeof(int32_t) * hptr.size(), cudaMemcpyHostToDevice, stream));
+    PBK_CUDA(cudaMemcpyAsync(dh.halo_rows.as(), hrows.data(), sizeof(int32_t) * hrows.size(), cudaMemcpyHostToDevice, stream));
+    PBK_CUDA(cudaMemcpyAsync(code_dev.as(), code.data(), sizeof(int32_t) * code.size(), cudaMemcpyHostToDevice, stream));
+    stats.h2d_bytes += static_cast<int64_t>(sizeof(int32_t) * (hptr.size() + hrows.size() + code.size()));
+    EllDev coded = dh.ell;
+    coded.col = code_dev.as<int32_t>();
+    dh.packed2.alloc(packed_ell_bytes(dtype, coded));
+    PBK_CUDA(launch_pack_ell(dtype, coded, dh.packed2.as(), stream));
+    PBK_CUDA(cudaStreamSynchronize(stream));
+}
+
 void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int order, Indices const& target) {
     require_hamiltonian();
     PBK_CUDA(cudaSetDevice(device));
@@ -430,6 +492,7 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
     if (order == ORDER_CLUSTER && bulk_stages >= 2) {  // row-major records for the bulk-copy staged step kernel
         dh.packed.alloc(packed_ell_bytes(dtype, dh.ell));
         PBK_CUDA(launch_pack_ell(dtype, dh.ell, dh.packed.as(), stream));
+        if (pair_mode) build_pair_metadata(dh, ell.col.data(), ell.pitch, ell.k);
     }
     PBK_CUDA(cudaStreamSynchronize(stream));
     dh.original_idx = target;
@@ -657,11 +720,12 @@ int Engine::pick_batch(int vectors, int extra_blocks) const {
     cudaMemGetInfo(&free_b, &total_b);
     // vec_a / vec_b (+ extra) blocks and the raw random words of one lane
     double const per_lane = static_cast<double>(n) * (dtype_size(dtype) * (2 + extra_blocks) + 4 * dtype_words(dtype));
-    double const reusable = static_cast<double>(vec_a.bytes() + vec_b.bytes() + raw.bytes());
+    double const reusable = static_cast<double>(vec_a.bytes() + vec_b.bytes() + vec_c.bytes() + vec_d.bytes() + raw.bytes());
     int cap = static_cast<int>((0.85 * static_cast<double>(free_b) + reusable) / per_lane);
     int const hard = 4096 / dtype_size(dtype);  // 256 chunks of 16 bytes per row
     cap = std::min(cap, hard);
     cap = std::min(cap, config.max_batch > 0 ? config.max_batch : 64);
+    if (pair_mode && pair_max_r > 0) cap = std::min(cap, pair_max_r);
     if (cap < 1) throw Error(PBK_RUNTIME_ERROR, "pbkpm: not enough device memory for one KPM vector pair");
     int const nb = (vectors + cap - 1) / cap;
     int rb = (vectors + nb - 1) / nb;
@@ -673,7 +737,7 @@ void Engine::ensure_moment_buffers(int R, int M) {
     mom.ensure(sizeof(double) * 2 * static_cast<size_t>(R) * M + 64);
     m01.ensure(sizeof(double) * 3 * R + 64);
     acc.ensure(sizeof(double) * 2 * M + 64);
-    partials.ensure(sizeof(double) * 3 * static_cast<size_t>(R) * max_step_blocks(num_sms));
+    partials.ensure(sizeof(double) * 2 * 3 * static_cast<size_t>(R) * max_step_blocks(num_sms));  // x2: the two-step kernel reduces two steps
     scratch.ensure(sizeof(double) * 2 * num_sms * 8);
 }
 
@@ -694,9 +758,38 @@ void Engine::step(DeviceHamiltonian const& h, const void* x, void* y, void* y2, 
     stats.step_bytes += static_cast<double>(nrows) * (h.ell.k * (s + 4.0) + static_cast<double>(R) * s * (2 + (subtract ? 1 : 0) + (y2 ? 1 : 0)));
 }
 
+bool Engine::step_pair(DeviceHamiltonian const& h, const void* a, const void* b, void* c, void* d, int R, int M, int nstep) {
+    PairArgs p;
+    p.packed = h.packed.as(); p.packed2 = h.packed2.as(); p.halo_ptr = h.halo_ptr.as<int32_t>(); p.halo_rows = h.halo_rows.as<int32_t>();
+    p.halo_max = h.halo_max;
+    p.a = a; p.b = b; p.c = c; p.d = d;
+    p.nrows = n; p.tile = h.tile; p.R = R; p.k = h.ell.k;
+    p.partials = partials.as<double>(); p.counter = counter.as<unsigned>(); p.mom = mom.as<double>(); p.m01 = m01.as<double>();
+    p.M = M; p.n = nstep; p.stages = pair_stages; p.blocks_per_sm = step_blocks_per_sm; p.min_blocks = pair_minb;
+    bool handled = false;
+    LaunchInfo info;
+    PBK_CUDA(launch_step_pair(dtype, p, num_sms, stream, &info, &handled));
+    if (!handled) return false;
+    ++launches;
+    ++stats.step_launches;
+    ++stats.pair_launches;
+    int const s = dtype_size(dtype);
+    stats.step_bytes += 2.0 * static_cast<double>(n) * (h.ell.k * (s + 4.0) + 3.0 * R * s);  // the per-step model, twice
+    return true;
+}
+
 void Engine::run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_size) {
     void* r0 = vec_a.as();
     void* r1 = vec_b.as();
+    // two-step kernel: full-system locality layout with halo metadata, and a halo fraction that leaves a gain
+    bool pair = pair_mode && !opt_size && h.packed2.bytes() && (h.halo_frac < 0.6 || pair_mode >= 2) && M / 2 >= 3;  // PBK_PAIR=2: regardless of the halo share
+    void* r2 = nullptr; void* r3 = nullptr;
+    if (pair) {
+        size_t const block_bytes = static_cast<size_t>(n) * R * dtype_size(dtype);
+        vec_c.ensure(block_bytes);
+        vec_d.ensure(block_bytes);
+        r2 = vec_c.as(); r3 = vec_d.as();
+    }
     PBK_CUDA(cudaEventRecord(ev2, stream));
     // r1 = 0.5 * H2 * r0, m0 = 0.5 |r0|^2, m1 = <r1|r0>     (make_r1 + collect.initial)
     int64_t init_rows = n;
@@ -706,6 +799,15 @@ void Engine::run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_siz
     }
     step(h, r0, r1, nullptr, init_rows, R, false, true, 0.5, M, 0, FIN_INIT);
     for (int k = 2; k <= M / 2; ++k) {  // calc_moments::basic (diagonal), calc_moments.hpp:36-51
+        if (pair && k + 1 <= M / 2) {   // r0 = r_{k-2}, r1 = r_{k-1}  ->  r2 = r_k, r3 = r_{k+1}
+            if (step_pair(h, r0, r1, r2, r3, R, M, k)) {
+                std::swap(r0, r2);
+                std::swap(r1, r3);
+                ++k;
+                continue;
+            }
+            pair = false;   // geometry not supported: single steps from here on
+        }
         int64_t const rows = opt_size ? h.map.optimal_size(k, M) : n;
         step(h, r1, r0, nullptr, rows, R, true, true, 1.0, M, k, FIN_STEP);
         std::swap(r0, r1);
@@ -873,7 +975,7 @@ void Engine::moments_dos(int M, int num_random, cd* out) {
     ensure_moment_buffers(1, M);
     PBK_CUDA(cudaMemsetAsync(acc.as(), 0, sizeof(double) * 2 * M, stream));
     if (count > 0) {
-        int const rb = pick_batch(count, 0);
+        int const rb = pick_batch(count, pair_mode ? 2 : 0);
         ensure_moment_buffers(rb, M);
         size_t const block_bytes = static_cast<size_t>(n) * rb * dtype_size(dtype);
         vec_a.ensure(block_bytes);
@@ -904,7 +1006,7 @@ void Engine::moments_diagonal(int M, const cd* r0, int count, cd* out) {
     auto& h = natural_hamiltonian();
     reset_stats(M, h, false, count);
     begin_moments();
-    int const rb = pick_batch(count, 0);
+    int const rb = pick_batch(count, pair_mode ? 2 : 0);
     ensure_moment_buffers(rb, M);
     size_t const block_bytes = static_cast<size_t>(n) * rb * dtype_size(dtype);
     vec_a.ensure(block_bytes);
@@ -982,7 +1084,7 @@ void Engine::moments_ldos(int M, const int32_t* idx, int nidx, cd* out) {
     shard(nidx, &first, &count);
     std::vector<cd> table(static_cast<size_t>(M) * nidx, cd(0, 0));
     if (count > 0) {
-        int const rb = pick_batch(count, 0);
+        int const rb = pick_batch(count, pair_mode ? 2 : 0);
         ensure_moment_buffers(rb, M);
         size_t const block_bytes = static_cast<size_t>(n) * rb * dtype_size(dtype);
         vec_a.ensure(block_bytes);

@@ -82,6 +82,10 @@ struct DeviceHamiltonian {
     std::vector<int32_t> reorder_map;  // original -> device row (empty: identity)
     DevBuf val, col, perm;
     DevBuf packed;                 // row-major packed copy of the ELL arrays for the bulk-copy staged step kernel (ORDER_CLUSTER only)
+    // two-step kernel (kernels_pair.cu): per-tile halo lists and the phase-2 records (column codes)
+    DevBuf packed2, halo_ptr, halo_rows;
+    int halo_max = 0;              // longest halo list (rows)
+    double halo_frac = 0;          // halo rows / rows: the redundant share of phase 1
     EllDev ell;
     double seconds = 0;
     uint64_t memory() const { return static_cast<uint64_t>(ell.rows) * ell.k * 0 + val.bytes() + col.bytes(); }
@@ -174,6 +178,8 @@ private:
     int bulk_stages = 4;         // pipeline depth of the bulk-copy staged step kernel (0: general kernel only)
     bool bulk_xstage = true;     // staged kernel: the CTA's own x rows go through shared memory too
     int64_t locality_tile = 0;   // rows per locality cluster of the full-system layout (0: keep the caller's order)
+    int pair_mode = 0;           // two Chebyshev steps per launch (kernels_pair.cu) where the layout allows it
+    int pair_stages = 4, pair_minb = 0, pair_max_r = 0;
     pbk_config config{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_begin = nullptr, ev_end = nullptr;
@@ -199,6 +205,7 @@ private:
     DeviceHamiltonian unscaled;   // original values, original order (Lanczos)
 
     // ---- work buffers ----
+    DevBuf vec_c, vec_d;         // second vector pair of the two-step kernel
     DevBuf vec_a, vec_b, vec_t, raw, mom, m01, acc, partials, counter, scratch, mt_state, mt_states, idx_buf;
     static constexpr int MT_MAX_SEGMENTS = 2048;
     uint64_t stream_pos = 0;     // next draw of the reference's random stream
@@ -230,6 +237,9 @@ private:
     void ensure_moment_buffers(int R, int M);
     void step(DeviceHamiltonian const& h, const void* x, void* y, void* y2, int64_t nrows, int R, bool subtract, bool sums,
               double scale, int M, int nstep, int fin);
+    /// two steps in one launch: c = H b - a, d = H c - b (moments of steps nstep and nstep + 1); false: not applicable
+    bool step_pair(DeviceHamiltonian const& h, const void* a, const void* b, void* c, void* d, int R, int M, int nstep);
+    void build_pair_metadata(DeviceHamiltonian& dh, const int32_t* col, int64_t pitch, int k);
     /// diagonal recursion for the R vectors in vec_a (r0); moments land in `mom` ([R][M] c128)
     void run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_size);
     /// off-diagonal recursion for the single vector in vec_a; `collect(n, r, half)` is called for every moment

@@ -64,6 +64,29 @@ constexpr int PACKED_PAD_ROWS = 256;
 void packed_record_layout(int scalar_bytes, int k, uint32_t* rec, uint32_t* valoff);
 size_t packed_ell_bytes(int dtype, EllDev const& h);
 cudaError_t launch_pack_ell(int dtype, EllDev const& h, void* packed, cudaStream_t s);
+/// K1b (kernels_pair.cu): two Chebyshev steps per launch, c = H b - a and d = H c - b, with the four fused sums.
+/// a, b are read, c, d written (four distinct N x R blocks).  `packed2` holds the phase-2 records whose column
+/// entries are codes (>= 0: global row of the tile itself, < 0: -(1 + slot) in the tile's halo list).
+struct PairArgs {
+    const void* packed = nullptr;
+    const void* packed2 = nullptr;
+    const int32_t* halo_ptr = nullptr;   // [tiles + 1]
+    const int32_t* halo_rows = nullptr;  // rows outside a tile that the tile's rows reference, ascending per tile
+    int halo_max = 0;                    // longest halo list
+    const void* a = nullptr; const void* b = nullptr; void* c = nullptr; void* d = nullptr;
+    int64_t nrows = 0;
+    int64_t tile = 0;
+    int R = 1, k = 0;
+    double* partials = nullptr;          // [2][grid][R*C]
+    unsigned* counter = nullptr;         // two counters
+    double* mom = nullptr; double* m01 = nullptr; int M = 0;
+    int n = 0;                           // moments of steps n and n + 1 are written
+    int stages = 4;
+    int blocks_per_sm = 0;
+    int min_blocks = 0;                  // register budget variant: 2 (<= 128 registers) or 3 (<= 80); 0 = by shared memory
+};
+/// *handled == false means "not applicable" (geometry, shared memory): the caller runs two single steps instead.
+cudaError_t launch_step_pair(int dtype, PairArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info, bool* handled);
 /// Upper bound of blocks launch_step may use (size of the partials buffer = this * R * 3 doubles)
 int max_step_blocks(int num_sms);
 

@@ -18,7 +18,7 @@
 //
 // Replaces, from the reference (cppcore/): compute::kpm_spmv_diagonal (include/compute/kernel_polynomial.hpp:288-323)
 // with the batching of DefaultCompute (src/kpm/default/Compute.cpp:52-88) and the Diagonal collectors.
-#include "step_common.cuh"
+#include "bulk_common.cuh"
 
 #include <map>
 #include <mutex>
@@ -28,33 +28,6 @@ namespace pbk {
 
 namespace {
 
-// ---- mbarrier / bulk-copy primitives ---------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    }
-}
-/// global -> shared bulk copy (16-byte granularity); signals `bar` with the number of bytes delivered
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(src)), "r"(bytes) : "memory");
-}
-
 struct BulkDev {  // kernel parameters
     const unsigned char* packed;  // row-major H records: int32 col[K] (padded), then T val[K]; `rec` bytes per row
     const void* x; void* y;
@@ -63,19 +36,6 @@ struct BulkDev {  // kernel parameters
     uint32_t rec, valoff, stage_bytes;
     double* partials; unsigned* counter; double* mom; double* m01; int M; int n; int fin;
 };
-
-// ---- explicit shared-space loads (32-bit addresses: no generic-address arithmetic in the hot loop) ----
-template<class CH> __device__ __forceinline__ CH lds_chunk(uint32_t addr) {
-    static_assert(sizeof(CH) == 16, "16-byte chunks");
-    int4 t;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(addr));
-    return *reinterpret_cast<CH*>(&t);
-}
-__device__ __forceinline__ int32_t lds_i32(uint32_t addr) { int32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ void lds_val(uint32_t addr, float& v) { asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); }
-__device__ __forceinline__ void lds_val(uint32_t addr, float2& v) { asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr)); }
-__device__ __forceinline__ void lds_val(uint32_t addr, double& v) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); }
-__device__ __forceinline__ void lds_val(uint32_t addr, double2& v) { asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr)); }
 
 template<class T, int V, int K, bool XS, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) cheb_step_bulk(BulkDev a) {

@@ -3,7 +3,7 @@
 
     python tools/step_sweep.py [--workload graphene_200nm_c64_dos] [--moments 130] [--vectors 64] CONFIG...
 CONFIG = comma-separated KEY=VALUE pairs, e.g.  PBK_TILE=-1  PBK_TILE=256,PBK_TPB=512
-Prints one line per config: ms per step launch, algorithmic GB/s, fraction of the measured HBM peak.
+Prints one line per config: ms per Chebyshev step (of one pass of `batch` vectors), algorithmic GB/s, fraction of the measured HBM peak.
 """
 import argparse
 import json
@@ -37,23 +37,26 @@ def main():
     ref = None
     for cfg in args.configs:
         env = dict(kv.split("=") for kv in cfg.split(",") if kv)
-        for k in ("PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL"):
+        max_batch = int(env.pop("MB", 0))   # pseudo-key: vectors per pass
+        for k in ("PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL", "PBK_BULK", "PBK_XS",
+                  "PBK_PAIR", "PBK_PAIR_STAGES", "PBK_PAIR_MINB", "PBK_PAIR_R"):
             os.environ.pop(k, None)
         os.environ.update(env)
         t0 = time.time()
-        kpm = pb.kpm(model, energy_range=w["energy_range"], silent=True)
+        kpm = pb.kpm(model, energy_range=w["energy_range"], silent=True, max_batch=max_batch)
         mom = None
         best = None
         for _ in range(args.reps + 1):
             mom = kpm.impl.moments_dos(args.moments, R)
             s = kpm.stats
-            ms = s.step_ms / s.step_launches
+            steps = s.step_launches + s.pair_launches   # a two-step launch advances the recursion twice
+            ms = s.step_ms / steps
             best = ms if best is None else min(best, ms)
-        gbs = s.step_bytes / s.step_launches / (best * 1e-3) / 1e9
+        gbs = s.step_bytes / steps / (best * 1e-3) / 1e9
         if ref is None:
             ref = mom
         err = float(np.abs(mom - ref).max() / np.abs(ref).max())
-        print(json.dumps(dict(config=cfg, ms_per_launch=round(best, 4), algorithmic_gbs=round(gbs, 1),
+        print(json.dumps(dict(config=cfg, ms_per_step=round(best, 4), pair_launches=int(s.pair_launches), vectors_per_ms=round(s.batch / best, 2), algorithmic_gbs=round(gbs, 1),
                               frac=round(gbs / peak, 4), hamiltonian_s=round(s.hamiltonian_time, 2),
                               starter_ms=round(s.starter_ms, 1), batch=s.batch, rel_diff_vs_first=err,
                               total_s=round(time.time() - t0, 1))), flush=True)
