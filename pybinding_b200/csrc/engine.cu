@@ -144,6 +144,7 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     step_prefetch_mask = static_cast<int>(env_int("PBK_PFMASK", 0));
     bulk_stages = static_cast<int>(env_int("PBK_BULK", 4));
     bulk_xstage = env_int("PBK_XS", 1) != 0;
+    cone_mode = static_cast<int>(env_int("PBK_CONE", 1));
     pair_mode = static_cast<int>(env_int("PBK_PAIR", 0));
     pair_stages = static_cast<int>(env_int("PBK_PAIR_STAGES", 4));
     pair_minb = static_cast<int>(env_int("PBK_PAIR_MINB", 0));
@@ -181,6 +182,7 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
     bfs_ready = BfsOrder();
     optimized = DeviceHamiltonian();
     unscaled = DeviceHamiltonian();
+    cone_gmap_rows = 0;
     have_bounds = false;
     lanczos_loops = 0;
     bounds_seconds = 0;
@@ -792,9 +794,10 @@ void Engine::run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_siz
     }
     PBK_CUDA(cudaEventRecord(ev2, stream));
     // r1 = 0.5 * H2 * r0, m0 = 0.5 |r0|^2, m1 = <r1|r0>     (make_r1 + collect.initial)
-    int64_t init_rows = n;
+    int64_t const nv = h.vec_rows > 0 ? h.vec_rows : n;
+    int64_t init_rows = nv;
     if (opt_size) {
-        PBK_CUDA(cudaMemsetAsync(r1, 0, static_cast<size_t>(n) * R * dtype_size(dtype), stream));
+        PBK_CUDA(cudaMemsetAsync(r1, 0, static_cast<size_t>(nv) * R * dtype_size(dtype), stream));
         init_rows = h.map.data[std::min(h.map.last_index(), h.map.src_offset + 1)];
     }
     step(h, r0, r1, nullptr, init_rows, R, false, true, 0.5, M, 0, FIN_INIT);
@@ -808,7 +811,7 @@ void Engine::run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_siz
             }
             pair = false;   // geometry not supported: single steps from here on
         }
-        int64_t const rows = opt_size ? h.map.optimal_size(k, M) : n;
+        int64_t const rows = opt_size ? h.map.optimal_size(k, M) : nv;
         step(h, r1, r0, nullptr, rows, R, true, true, 1.0, M, k, FIN_STEP);
         std::swap(r0, r1);
     }
@@ -1048,11 +1051,193 @@ void Engine::random_vectors(int count, cd* out) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// LDOS on light-cone sub-systems.  A unit vector at site i spreads one breadth-first shell per Chebyshev step, and the
+// diagonal algorithm stops at step M/2, so <i|T_n(H~)|i> for n < M only involves the sites within M/2 bonds of i.  The
+// reference relabels the *whole* system from i on the host for every site (OptimizedHamiltonian::create_reordered) and
+// then touches only `optimal_size(n)` rows per step.  Here the host only walks the ball itself (truncated BFS, same
+// visiting order), the ball's rows are cut out of the device-resident scaled ELL by a kernel, and the recursion runs on
+// that sub-system with the same slice map -- identical arithmetic per row, no per-site pass over the full system.
+// ------------------------------------------------------------------------------------------------
+SliceMap Cone::map() const {
+    SliceMap m;
+    m.data = borders;
+    if (!exhausted && m.data.size() > 1) m.data.pop_back();   // rows of the outermost shell miss neighbours: never processed
+    m.src_offset = 0;
+    m.dest_offset = 0;
+    return m;
+}
+
+Cone Engine::bfs_cone(int32_t src, int depth, std::vector<int32_t>& mark) const {
+    Cone c;
+    c.queue.push_back(src);
+    mark[src] = 0;
+    c.borders = {1};
+    size_t head = 0;
+    for (int shell = 0; shell < depth; ++shell) {
+        size_t const end = c.queue.size();
+        for (; head < end; ++head) {
+            int32_t const row = c.queue[head];
+            for (int p = h_indptr[row]; p < h_indptr[row + 1]; ++p) {
+                int32_t const col = h_indices[p];
+                if (mark[col] < 0) { mark[col] = static_cast<int32_t>(c.queue.size()); c.queue.push_back(col); }
+            }
+        }
+        if (c.queue.size() == end) { c.exhausted = true; break; }
+        c.borders.push_back(static_cast<int32_t>(c.queue.size()));
+    }
+    for (int32_t site : c.queue) mark[site] = -1;
+    return c;
+}
+
+bool Engine::moments_ldos_cones(int M, Indices const& target, cd* out) {
+    int const nidx = static_cast<int>(target.src.size());
+    int const depth = M / 2;
+    auto& hn = natural_hamiltonian();
+    int const s = dtype_size(dtype);
+    int const kell = hn.ell.k;
+    auto half_rows = [&](SliceMap const& m) {   // rows processed by one diagonal calculation (Stats.cpp:31-47: halved)
+        double sum = 0;
+        for (int k = 0; k < M; ++k) sum += static_cast<double>(m.optimal_size(k, M));
+        return sum / 2;
+    };
+    // cost model on the first site (every rank looks at the same one): per-site cones against full-system batches
+    std::vector<std::vector<int32_t>> marks(1, std::vector<int32_t>(static_cast<size_t>(n), -1));
+    Cone first_cone = bfs_cone(target.src[0], depth, marks[0]);
+    if (first_cone.exhausted && static_cast<int64_t>(first_cone.queue.size()) < n) {
+        throw Error(PBK_RUNTIME_ERROR, "KPM: the Hamiltonian graph is not connected; the optimal_size "
+                                       "reordering needs a connected system");
+    }
+    if (nidx > 1) {
+        // one launch per step either way: a launch costs at least the launch latency, else its bytes at the rate the
+        // kernel reaches (scalar general kernel on a cone / staged kernel on the full system)
+        double const t_launch = 5e-6, bw_cone = 3e12, bw_full = 5e12;
+        int const steps = M / 2;
+        double const cone_step_bytes = half_rows(first_cone.map()) / steps * (kell * (s + 4.0) + 3.0 * s);
+        double const cone_time = static_cast<double>(nidx) * steps * std::max(t_launch, cone_step_bytes / bw_cone);
+        int const rb = std::min(nidx, 64);
+        double const full_step_bytes = static_cast<double>(n) * (kell * (s + 4.0) + 3.0 * rb * s);
+        double const full_time = std::ceil(nidx / 64.0) * steps * std::max(t_launch, full_step_bytes / bw_full);
+        if (cone_time >= full_time) return false;
+    }
+
+    int64_t const h2d0 = stats.h2d_bytes;
+    stats = pbk_stats{};
+    stats.h2d_bytes = h2d0;
+    stats.num_moments = M;
+    stats.multiplier = nidx;
+    stats.nnz = static_cast<uint64_t>(M) * n * kell / 2;
+    stats.vec = static_cast<uint64_t>(M) * n / 2;
+    stats.matrix_memory = static_cast<uint64_t>(n) * kell * (s + 4);
+    stats.vector_memory = static_cast<uint64_t>(n) * s;
+    stats.hamiltonian_time = hn.seconds;
+    stats.batch = 1;
+    launches = 0;
+
+    begin_moments();
+    progress(-1, nidx);
+    int first = 0, count = 0;
+    shard(nidx, &first, &count);
+    std::vector<cd> table(static_cast<size_t>(M) * nidx, cd(0, 0));
+    if (cone_gmap_rows != n) {
+        cone_gmap.ensure(sizeof(int32_t) * n);
+        PBK_CUDA(cudaMemsetAsync(cone_gmap.as(), 0xff, sizeof(int32_t) * n, stream));
+        cone_gmap_rows = n;
+    }
+    ensure_moment_buffers(1, M);
+    cone_table.ensure(sizeof(cd) * static_cast<size_t>(M) * std::max(count, 1));
+    const int32_t* perm = hn.reordered ? hn.perm.as<int32_t>() : nullptr;
+    double opt_rows = 0;
+    bool full = false;
+    int const chunk = 32;
+    int const nthreads = std::max(1, std::min<int>({static_cast<int>(std::thread::hardware_concurrency()), 16, count}));
+    marks.resize(std::min(nthreads, chunk), std::vector<int32_t>(static_cast<size_t>(n), -1));
+    for (int c0 = 0; c0 < count; c0 += chunk) {
+        int const nc = std::min(chunk, count - c0);
+        std::vector<Cone> cones(nc);
+        {   // host: the balls of this chunk, one thread per site
+            std::vector<std::thread> pool;
+            int const nt = std::min<int>(static_cast<int>(marks.size()), nc);
+            for (int t = 0; t < nt; ++t) {
+                pool.emplace_back([&, t] {
+                    for (int j = t; j < nc; j += nt) {
+                        int32_t const site = target.src[first + c0 + j];
+                        if (first + c0 + j == 0) cones[j] = first_cone;
+                        else cones[j] = bfs_cone(site, depth, marks[t]);
+                    }
+                });
+            }
+            for (auto& th : pool) th.join();
+        }
+        for (int j = 0; j < nc; ++j) {
+            Cone const& cone = cones[j];
+            int64_t const nloc = static_cast<int64_t>(cone.queue.size());
+            int64_t const rows = cone.complete_rows();
+            int64_t const pitch = (rows + 31) / 32 * 32;
+            cone_queue.ensure(sizeof(int32_t) * nloc);
+            cone_val.ensure(static_cast<size_t>(kell) * pitch * s);
+            cone_col.ensure(static_cast<size_t>(kell) * pitch * sizeof(int32_t));
+            PBK_CUDA(cudaMemcpyAsync(cone_queue.as(), cone.queue.data(), sizeof(int32_t) * nloc, cudaMemcpyHostToDevice, stream));
+            stats.h2d_bytes += static_cast<int64_t>(sizeof(int32_t) * nloc);
+            PBK_CUDA(launch_cone_mark(cone_queue.as<int32_t>(), nloc, perm, cone_gmap.as<int32_t>(), true, stream));
+            PBK_CUDA(launch_cone_extract(dtype, hn.ell, cone_queue.as<int32_t>(), perm, cone_gmap.as<int32_t>(), rows, cone_val.as(),
+                                         cone_col.as<int32_t>(), pitch, stream));
+            PBK_CUDA(launch_cone_mark(cone_queue.as<int32_t>(), nloc, perm, cone_gmap.as<int32_t>(), false, stream));
+            launches += 3;
+
+            DeviceHamiltonian hc;   // a view: the buffers stay with the engine
+            hc.ell = EllDev{cone_val.as(), cone_col.as<int32_t>(), rows, pitch, kell};
+            hc.map = cone.map();
+            hc.idx = Indices{{0}, {0}};
+            hc.sliced = true;
+            hc.vec_rows = nloc;
+            hc.valid = true;
+            size_t const vbytes = static_cast<size_t>(nloc) * s;
+            vec_a.ensure(vbytes);
+            vec_b.ensure(vbytes);
+            idx_buf.ensure(sizeof(int32_t));
+            PBK_CUDA(cudaMemsetAsync(idx_buf.as(), 0, sizeof(int32_t), stream));   // the source is position 0 of its own ball
+            PBK_CUDA(launch_unit_starter(dtype, vec_a.as(), nloc, 1, idx_buf.as<int32_t>(), 1, stream));
+            launches += 1;
+            run_diagonal(hc, 1, M, true);
+            PBK_CUDA(cudaMemcpyAsync(cone_table.as<cd>() + static_cast<size_t>(c0 + j) * M, mom.as(), sizeof(cd) * M, cudaMemcpyDeviceToDevice, stream));
+            opt_rows += half_rows(hc.map);
+            full = full || hc.map.uses_full_system(M);
+            ++stats.num_batches;
+            progress(1, nidx);
+        }
+    }
+    if (count > 0) {
+        std::vector<cd> host(static_cast<size_t>(count) * M);
+        PBK_CUDA(cudaMemcpyAsync(host.data(), cone_table.as(), sizeof(cd) * host.size(), cudaMemcpyDeviceToHost, stream));
+        PBK_CUDA(cudaStreamSynchronize(stream));
+        stats.d2h_bytes += static_cast<int64_t>(sizeof(cd) * host.size());
+        for (int j = 0; j < count; ++j) for (int k = 0; k < M; ++k) table[static_cast<size_t>(k) * nidx + first + j] = host[static_cast<size_t>(j) * M + k];
+    }
+    if (world > 1) {
+        DevBuf t(sizeof(cd) * table.size());
+        PBK_CUDA(cudaMemcpyAsync(t.as(), table.data(), sizeof(cd) * table.size(), cudaMemcpyHostToDevice, stream));
+        allreduce(t.as<double>(), static_cast<int64_t>(2 * table.size()));
+        PBK_CUDA(cudaMemcpyAsync(table.data(), t.as(), sizeof(cd) * table.size(), cudaMemcpyDeviceToHost, stream));
+        PBK_CUDA(cudaStreamSynchronize(stream));
+    }
+    std::copy(table.begin(), table.end(), out);
+    stats.opt_vec = static_cast<uint64_t>(opt_rows / std::max(count, 1));
+    stats.opt_nnz = stats.opt_vec * kell;
+    stats.uses_full_system = full;
+    end_moments();
+    progress(nidx, nidx);
+    return true;
+}
+
 void Engine::moments_ldos(int M, const int32_t* idx, int nidx, cd* out) {
     check_num_moments(M);
     if (nidx < 1) throw Error(PBK_INVALID_ARGUMENT, "at least one index is required");
     for (int i = 0; i < nidx; ++i) if (idx[i] < 0 || idx[i] >= n) throw Error(PBK_INVALID_ARGUMENT, "LDOS index out of range");
     Indices target{std::vector<int32_t>(idx, idx + nidx), std::vector<int32_t>(idx, idx + nidx)};
+    // per-site light-cone sub-systems cut out of the resident Hamiltonian, unless many small launches would cost more
+    // than advancing all the unit vectors together (then: the reference's relabelling from src[0], or the full-system batch)
+    if (config.optimal_size && cone_mode && moments_ldos_cones(M, target, out)) return;
     // Light-cone slicing pays when the sources sit together (one site, the orbitals of a site, a small region).
     // For sources spread over the sample the union of the light cones is the whole system from the first steps on:
     // then the full-system locality layout with the staged kernel is the faster way to advance the unit vectors.

@@ -76,6 +76,7 @@ struct DeviceHamiltonian {
     bool reordered = false;        // rows are relabelled: reorder_map / perm are set
     bool sliced = false;           // BFS order from the source: `map` holds the light-cone slices
     int64_t tile = 0;              // ORDER_CLUSTER: rows per locality cluster (the step kernel's CTA tile), else 0
+    int64_t vec_rows = 0;          // length of a KPM vector on this layout (0: the system size); light-cone sub-systems are shorter
     std::vector<int32_t> order_queue;  // device row -> original (ORDER_CLUSTER only)
     Indices original_idx, idx;     // idx: positions in the device ordering
     SliceMap map;
@@ -99,6 +100,18 @@ struct BfsOrder {
     std::vector<int32_t> reorder_map;  // original -> new
     SliceMap map;
     bool valid_for(Indices const& t) const { return valid && target == t; }
+};
+
+/// Light cone of one source site: the breadth-first ball that the recursion can reach in `depth` steps.
+/// queue[i] = original site at position i (shell by shell, the reference's BFS order: OptimizedHamiltonian.cpp:88-143),
+/// borders[j] = number of sites within graph distance j.
+struct Cone {
+    std::vector<int32_t> queue;
+    std::vector<int32_t> borders;
+    bool exhausted = false;        // the ball is the whole connected component: every row has its full neighbourhood
+    /// rows whose neighbours are all inside the ball
+    int64_t complete_rows() const { return exhausted || borders.size() < 2 ? static_cast<int64_t>(queue.size()) : borders[borders.size() - 2]; }
+    SliceMap map() const;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -206,6 +219,9 @@ private:
 
     // ---- work buffers ----
     DevBuf vec_c, vec_d;         // second vector pair of the two-step kernel
+    DevBuf cone_val, cone_col, cone_queue, cone_gmap, cone_table;   // light-cone sub-system of the site being processed
+    int64_t cone_gmap_rows = 0;  // cone_gmap holds -1 for this many rows
+    int cone_mode = 1;           // PBK_CONE=0: the previous host-side full BFS relabelling for LDOS
     DevBuf vec_a, vec_b, vec_t, raw, mom, m01, acc, partials, counter, scratch, mt_state, mt_states, idx_buf;
     static constexpr int MT_MAX_SEGMENTS = 2048;
     uint64_t stream_pos = 0;     // next draw of the reference's random stream
@@ -228,6 +244,9 @@ private:
     DeviceHamiltonian& natural_hamiltonian();
     DeviceHamiltonian& optimized_for(Indices const& target);
     DeviceHamiltonian& unscaled_hamiltonian();
+    Cone bfs_cone(int32_t src, int depth, std::vector<int32_t>& mark) const;
+    /// LDOS moments on per-site light-cone sub-systems cut out of the resident Hamiltonian; false: the full-system batch is cheaper
+    bool moments_ldos_cones(int M, Indices const& target, cd* out);
     void upload_operator(DeviceHamiltonian& dh, const float* positions, DeviceHamiltonian const& like);  // velocity operator
     void upload_csr_operator(DeviceHamiltonian& dh, int64_t rows, const int32_t* indptr, const int32_t* indices, const cd* data,
                              DeviceHamiltonian const& like);

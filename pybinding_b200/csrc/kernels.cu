@@ -387,6 +387,38 @@ __global__ void extract_lane_kernel(const T* v, int64_t n, int R, int lane, cons
     out[2 * i] = re_(e); out[2 * i + 1] = im_(e);
 }
 
+// ---- light-cone sub-systems ("cones") of the unit-vector quantities ---------------------------
+/// gmap[row of site queue[i] in the resident layout] = set ? i : -1
+__global__ void cone_mark_kernel(const int32_t* __restrict__ queue, int64_t count, const int32_t* __restrict__ perm, int32_t* gmap, int set) {
+    int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    int32_t const site = queue[i];
+    gmap[perm ? perm[site] : site] = set ? static_cast<int32_t>(i) : -1;
+}
+
+/// rows [0, rows) of the sub-system: the resident ELL row of site queue[i] with its columns relabelled through gmap.
+/// Columns outside the cone cannot occur for rows whose whole neighbourhood was visited; they are neutralised anyway.
+template<class T>
+__global__ void cone_extract_kernel(const T* __restrict__ val, const int32_t* __restrict__ col, int64_t pitch, int k,
+                                    const int32_t* __restrict__ queue, const int32_t* __restrict__ perm, const int32_t* __restrict__ gmap,
+                                    int64_t rows, T* __restrict__ out_val, int32_t* __restrict__ out_col, int64_t out_pitch) {
+    int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= out_pitch) return;
+    if (i >= rows) {
+        for (int s = 0; s < k; ++s) { out_val[s * out_pitch + i] = zero_(T{}); out_col[s * out_pitch + i] = 0; }
+        return;
+    }
+    int32_t const site = queue[i];
+    int64_t const g = perm ? perm[site] : site;
+    for (int s = 0; s < k; ++s) {
+        T v = val[s * pitch + g];
+        int32_t lc = gmap[col[s * pitch + g]];
+        if (lc < 0) { lc = static_cast<int32_t>(i); v = zero_(T{}); }
+        out_val[s * out_pitch + i] = v;
+        out_col[s * out_pitch + i] = lc;
+    }
+}
+
 // ---- Lanczos -----------------------------------------------------------------------------------
 template<class T> __device__ __forceinline__ T axpy_(double a, T x, T y);  // y - a*x
 template<> __device__ __forceinline__ float axpy_(double a, float x, float y) { return y - static_cast<float>(a) * x; }
@@ -467,6 +499,20 @@ cudaError_t launch_scatter_block(int dtype, const double* src_c128, int64_t n, i
 cudaError_t launch_extract_lane(int dtype, const void* v, int64_t n, int R, int lane, const int32_t* perm_dev, double* out_c128, cudaStream_t s) {
     int const grid = static_cast<int>((n + 255) / 256);
     PBK_DISPATCH(dtype, (extract_lane_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(v), n, R, lane, perm_dev, out_c128)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cone_mark(const int32_t* queue_dev, int64_t count, const int32_t* perm_dev, int32_t* gmap, bool set, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    cone_mark_kernel<<<static_cast<int>((count + 255) / 256), 256, 0, s>>>(queue_dev, count, perm_dev, gmap, set ? 1 : 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cone_extract(int dtype, EllDev const& h, const int32_t* queue_dev, const int32_t* perm_dev, const int32_t* gmap,
+                                int64_t rows, void* out_val, int32_t* out_col, int64_t out_pitch, cudaStream_t s) {
+    int const grid = static_cast<int>((out_pitch + 255) / 256);
+    PBK_DISPATCH(dtype, (cone_extract_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(h.val), h.col, h.pitch, h.k, queue_dev, perm_dev, gmap,
+                                                                      rows, static_cast<T*>(out_val), out_col, out_pitch)));
     return cudaGetLastError();
 }
 

@@ -107,6 +107,14 @@ cudaError_t launch_scatter_block(int dtype, const double* src_c128, int64_t n, i
 /// out c128[i] = v[(perm ? perm[i] : i) * R + lane]
 cudaError_t launch_extract_lane(int dtype, const void* v, int64_t n, int R, int lane, const int32_t* perm_dev, double* out_c128, cudaStream_t s);
 
+// ---- light-cone sub-systems of LDOS (kernels.cu) ------------------------------------------------
+/// gmap[resident row of site queue[i]] = set ? i : -1   (perm_dev: site -> resident row, or null)
+cudaError_t launch_cone_mark(const int32_t* queue_dev, int64_t count, const int32_t* perm_dev, int32_t* gmap, bool set, cudaStream_t s);
+/// Sub-ELL of the first `rows` sites of `queue` (slot-major, pitch `out_pitch`, columns = positions in `queue`) cut out
+/// of the resident scaled ELL `h`; rows [rows, out_pitch) are zero padding.
+cudaError_t launch_cone_extract(int dtype, EllDev const& h, const int32_t* queue_dev, const int32_t* perm_dev, const int32_t* gmap,
+                                int64_t rows, void* out_val, int32_t* out_col, int64_t out_pitch, cudaStream_t s);
+
 // ---- random starters (mt19937.cu) ------------------------------------------------------------
 constexpr int MT_N = 624;
 /// state_dev: 624 words + 1 position word.  Seeds std::mt19937's default state (seed 5489, position 624).

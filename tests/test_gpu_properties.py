@@ -24,7 +24,7 @@ pytestmark = pytest.mark.gpu
 TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.complex64): 1e-5,
        np.dtype(np.float64): 1e-11, np.dtype(np.complex128): 1e-11}
 KNOBS = ("PBK_BULK", "PBK_XS", "PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL",
-         "PBK_PAIR", "PBK_PAIR_STAGES", "PBK_PAIR_MINB", "PBK_PAIR_R")
+         "PBK_PAIR", "PBK_PAIR_STAGES", "PBK_PAIR_MINB", "PBK_PAIR_R", "PBK_CONE")
 
 
 @contextmanager
@@ -224,3 +224,45 @@ def test_spread_ldos_sites_use_full_system_layout_and_match_single_site_runs():
     for j, site in enumerate(near):
         one = kpm.impl.moments_ldos(M, [site])[:, 0]
         assert np.abs(both[:, j] - one).max() / np.abs(one).max() < 1e-11
+
+
+def ldos_moments(model, energy_range, M, sites, **kw):
+    with knobs(**kw):
+        kpm = pb.kpm(model, energy_range=energy_range, silent=True)
+        return kpm.impl.moments_ldos(M, sites), kpm.stats
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.complex64, np.float64, np.complex128], ids=lambda d: np.dtype(d).name)
+def test_cone_ldos_equals_full_relabelling(dtype):
+    """LDOS on the light-cone sub-system cut out of the resident Hamiltonian (moments_ldos_cones) against the
+    reference's scheme (relabel the whole system from the source on the host, OptimizedHamiltonian.cpp:88-143):
+    same slices, same rows, same moments."""
+    dtype = np.dtype(dtype)
+    model = pb.graphene_rectangle(25.0, dtype=dtype, onsite=0.2, magnetic_field=150.0 if dtype.kind == "c" else 0.0)
+    site = model.system.find_nearest([1.0, -2.0])
+    corner = model.system.find_nearest([-12.5, -12.5])
+    for M in (34, 130, 514):        # light cone inside the sample, touching the edges, covering the whole sample
+        for src in (site, corner):
+            old, s0 = ldos_moments(model, (-9, 9), M, [src], PBK_CONE=0)
+            new, s1 = ldos_moments(model, (-9, 9), M, [src])
+            assert s1.opt_nnz == s0.opt_nnz and s1.nnz == s0.nnz, (M, src)
+            assert s1.step_launches == s0.step_launches == M // 2
+            assert rel_err(new, old) < (1e-12 if dtype in (np.float64, np.complex128) else 2e-6), (M, src)
+    expected = OracleKPM(model.hamiltonian, energy_range=(-9, 9), hp=True).ldos_moments(130, [site])
+    new, _ = ldos_moments(model, (-9, 9), 130, [site])
+    assert rel_err(new, expected) < TOL[dtype]
+
+
+def test_cone_ldos_many_sites_of_a_large_system():
+    """Several sites of a large sample: each one runs on its own light-cone sub-system (no pass over the full system)"""
+    model = pb.graphene_rectangle(200.0, dtype=np.float64, onsite=0.1)    # 1.5 M sites
+    fn = model.system.find_nearest
+    sites = [fn([-60, 10]), fn([0, 0]), fn([99.9, -99.9]), fn([35, 70])]
+    M = 130
+    batch, s = ldos_moments(model, (-9, 9), M, sites)
+    assert s.num_batches == len(sites) and s.bulk_launches == 0 and s.batch == 1
+    assert s.opt_nnz < s.nnz / 50
+    for j, site in enumerate(sites):
+        one, s0 = ldos_moments(model, (-9, 9), M, [site], PBK_CONE=0)
+        assert np.abs(batch[:, j] - one[:, 0]).max() / np.abs(one).max() < 1e-12
+    assert np.all(batch[0].real == 0.5) and np.all(batch.imag == 0)
