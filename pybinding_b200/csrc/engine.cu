@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
@@ -145,6 +146,8 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     bulk_stages = static_cast<int>(env_int("PBK_BULK", 4));
     bulk_xstage = env_int("PBK_XS", 1) != 0;
     cone_mode = static_cast<int>(env_int("PBK_CONE", 1));
+    graph_mode = static_cast<int>(env_int("PBK_GRAPH", 1));
+    graph_max_bytes = 1e6 * static_cast<double>(env_int("PBK_GRAPH_MAX_MB", 64));
     pair_mode = static_cast<int>(env_int("PBK_PAIR", 0));
     pair_stages = static_cast<int>(env_int("PBK_PAIR_STAGES", 4));
     pair_minb = static_cast<int>(env_int("PBK_PAIR_MINB", 0));
@@ -156,8 +159,14 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     mt_state.alloc(sizeof(uint32_t) * (MT_N + 8));
 }
 
+void Engine::clear_graphs() {
+    for (auto& kv : graph_cache) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    graph_cache.clear();
+}
+
 Engine::~Engine() {
     cudaSetDevice(device);
+    clear_graphs();
     comm_destroy();
     for (cudaEvent_t e : {ev0, ev1, ev2, ev3, ev_begin, ev_end}) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
@@ -178,6 +187,7 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
     h_indices.assign(indices, indices + nnz);
     h_data.assign(static_cast<const char*>(data), static_cast<const char*>(data) + nnz * dtype_size(dt));
     has_h = true;
+    clear_graphs();
     natural = DeviceHamiltonian();
     bfs_ready = BfsOrder();
     optimized = DeviceHamiltonian();
@@ -793,28 +803,75 @@ void Engine::run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_siz
         r2 = vec_c.as(); r3 = vec_d.as();
     }
     PBK_CUDA(cudaEventRecord(ev2, stream));
-    // r1 = 0.5 * H2 * r0, m0 = 0.5 |r0|^2, m1 = <r1|r0>     (make_r1 + collect.initial)
     int64_t const nv = h.vec_rows > 0 ? h.vec_rows : n;
-    int64_t init_rows = nv;
-    if (opt_size) {
-        PBK_CUDA(cudaMemsetAsync(r1, 0, static_cast<size_t>(nv) * R * dtype_size(dtype), stream));
-        init_rows = h.map.data[std::min(h.map.last_index(), h.map.src_offset + 1)];
-    }
-    step(h, r0, r1, nullptr, init_rows, R, false, true, 0.5, M, 0, FIN_INIT);
-    for (int k = 2; k <= M / 2; ++k) {  // calc_moments::basic (diagonal), calc_moments.hpp:36-51
-        if (pair && k + 1 <= M / 2) {   // r0 = r_{k-2}, r1 = r_{k-1}  ->  r2 = r_k, r3 = r_{k+1}
-            if (step_pair(h, r0, r1, r2, r3, R, M, k)) {
-                std::swap(r0, r2);
-                std::swap(r1, r3);
-                ++k;
-                continue;
-            }
-            pair = false;   // geometry not supported: single steps from here on
+    auto emit = [&]() {
+        // r1 = 0.5 * H2 * r0, m0 = 0.5 |r0|^2, m1 = <r1|r0>     (make_r1 + collect.initial)
+        int64_t init_rows = nv;
+        if (opt_size) {
+            PBK_CUDA(cudaMemsetAsync(r1, 0, static_cast<size_t>(nv) * R * dtype_size(dtype), stream));
+            init_rows = h.map.data[std::min(h.map.last_index(), h.map.src_offset + 1)];
         }
-        int64_t const rows = opt_size ? h.map.optimal_size(k, M) : nv;
-        step(h, r1, r0, nullptr, rows, R, true, true, 1.0, M, k, FIN_STEP);
-        std::swap(r0, r1);
+        step(h, r0, r1, nullptr, init_rows, R, false, true, 0.5, M, 0, FIN_INIT);
+        for (int k = 2; k <= M / 2; ++k) {  // calc_moments::basic (diagonal), calc_moments.hpp:36-51
+            if (pair && k + 1 <= M / 2) {   // r0 = r_{k-2}, r1 = r_{k-1}  ->  r2 = r_k, r3 = r_{k+1}
+                if (step_pair(h, r0, r1, r2, r3, R, M, k)) {
+                    std::swap(r0, r2);
+                    std::swap(r1, r3);
+                    ++k;
+                    continue;
+                }
+                pair = false;   // geometry not supported: single steps from here on
+            }
+            int64_t const rows = opt_size ? h.map.optimal_size(k, M) : nv;
+            step(h, r1, r0, nullptr, rows, R, true, true, 1.0, M, k, FIN_STEP);
+            std::swap(r0, r1);
+        }
+    };
+    // Small systems are launch-bound (a step is a few microseconds of work): capture the whole sequence once as a
+    // CUDA graph and replay it on later runs with the same buffers and row counts.
+    bool const graphable = graph_mode && !pair && !h.transient && M / 2 >= 8 &&
+                           static_cast<double>(nv) * R * dtype_size(dtype) <= graph_max_bytes;
+    bool done = false;
+    if (graphable) {
+        std::vector<int64_t> key = {reinterpret_cast<int64_t>(h.ell.val), reinterpret_cast<int64_t>(h.ell.col), reinterpret_cast<int64_t>(h.packed.as()),
+                                    reinterpret_cast<int64_t>(r0), reinterpret_cast<int64_t>(r1), reinterpret_cast<int64_t>(mom.as()),
+                                    reinterpret_cast<int64_t>(partials.as()), reinterpret_cast<int64_t>(m01.as()), reinterpret_cast<int64_t>(counter.as()),
+                                    h.ell.pitch, h.ell.k, h.tile, R, M, opt_size ? 1 : 0, nv, dtype, step_tpb, step_blocks_per_sm, step_prefetch,
+                                    bulk_stages, bulk_xstage ? 1 : 0};
+        if (opt_size) for (int k = 1; k <= M / 2; ++k) key.push_back(h.map.optimal_size(k, M));
+        auto it = graph_cache.find(key);
+        if (it == graph_cache.end()) {
+            if (graph_cache.size() >= 16) clear_graphs();
+            RecursionGraph g;
+            int64_t const l0 = launches, s0 = stats.step_launches, b0 = stats.bulk_launches;
+            double const by0 = stats.step_bytes;
+            void* const k0 = r0; void* const k1 = r1;
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                bool ok = true;
+                try { emit(); } catch (Error const&) { ok = false; }
+                cudaError_t const end = cudaStreamEndCapture(stream, &graph);
+                if (ok && end == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+                    g.launches = launches - l0; g.step_launches = stats.step_launches - s0; g.bulk_launches = stats.bulk_launches - b0;
+                    g.step_bytes = stats.step_bytes - by0;
+                    it = graph_cache.emplace(std::move(key), g).first;
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+            // the capture only recorded the launches: undo its bookkeeping, the replay below (or the direct run) redoes it
+            launches = l0; stats.step_launches = s0; stats.bulk_launches = b0; stats.step_bytes = by0;
+            r0 = k0; r1 = k1;
+            if (it == graph_cache.end()) { cudaGetLastError(); graph_mode = 0; }   // capture unsupported here: plain launches from now on
+        }
+        if (it != graph_cache.end()) {
+            PBK_CUDA(cudaGraphLaunch(it->second.exec, stream));
+            launches += it->second.launches; stats.step_launches += it->second.step_launches; stats.bulk_launches += it->second.bulk_launches;
+            stats.step_bytes += it->second.step_bytes;
+            ++stats.graph_launches;
+            done = true;
+        }
     }
+    if (!done) emit();
     PBK_CUDA(cudaEventRecord(ev3, stream));
     PBK_CUDA(cudaEventSynchronize(ev3));
     float ms = 0;
@@ -1114,7 +1171,8 @@ bool Engine::moments_ldos_cones(int M, Indices const& target, cd* out) {
         double const t_launch = 5e-6, bw_cone = 3e12, bw_full = 5e12;
         int const steps = M / 2;
         double const cone_step_bytes = half_rows(first_cone.map()) / steps * (kell * (s + 4.0) + 3.0 * s);
-        double const cone_time = static_cast<double>(nidx) * steps * std::max(t_launch, cone_step_bytes / bw_cone);
+        int const grp = std::min(nidx, 32);   // sub-systems advanced by one launch (bounded by memory later on)
+        double const cone_time = std::ceil(static_cast<double>(nidx) / grp) * steps * std::max(t_launch, grp * cone_step_bytes / bw_cone);
         int const rb = std::min(nidx, 64);
         double const full_step_bytes = static_cast<double>(n) * (kell * (s + 4.0) + 3.0 * rb * s);
         double const full_time = std::ceil(nidx / 64.0) * steps * std::max(t_launch, full_step_bytes / bw_full);
@@ -1149,63 +1207,121 @@ bool Engine::moments_ldos_cones(int M, Indices const& target, cd* out) {
     const int32_t* perm = hn.reordered ? hn.perm.as<int32_t>() : nullptr;
     double opt_rows = 0;
     bool full = false;
-    int const chunk = 32;
-    int const nthreads = std::max(1, std::min<int>({static_cast<int>(std::thread::hardware_concurrency()), 16, count}));
-    marks.resize(std::min(nthreads, chunk), std::vector<int32_t>(static_cast<size_t>(n), -1));
-    for (int c0 = 0; c0 < count; c0 += chunk) {
-        int const nc = std::min(chunk, count - c0);
+    int const steps = M / 2;
+    constexpr int C_MAX = 3;
+    int const blocks_cap = num_sms * 4;   // blocks per sub-system and launch
+
+    // group size: sub-systems advanced together by one launch per step, bounded by device memory
+    auto slot_bytes = [&](Cone const& c) {
+        int64_t const rows = c.complete_rows();
+        int64_t const pitch = (rows + 31) / 32 * 32;
+        return static_cast<double>(kell) * pitch * (s + 4.0) + 2.0 * static_cast<double>(c.queue.size()) * s + 4.0 * c.queue.size();
+    };
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    double const budget = std::min(0.4 * static_cast<double>(free_b) + static_cast<double>(cone_val.bytes() + cone_col.bytes() + vec_a.bytes()), 16e9);
+    int group = static_cast<int>(std::max(1.0, std::min(64.0, budget / (1.25 * slot_bytes(first_cone)))));
+    group = std::max(1, std::min(group, count));
+    int const nthreads = std::max(1, std::min<int>({static_cast<int>(std::thread::hardware_concurrency()), 16, group}));
+    marks.resize(nthreads, std::vector<int32_t>(static_cast<size_t>(n), -1));
+    stats.batch = group;
+    DevBuf slots_dev(sizeof(ConeSlot) * group), rows_dev(sizeof(int32_t) * static_cast<size_t>(group) * (steps + 1)),
+           m01_dev(sizeof(double) * 3 * group), counters_dev(sizeof(unsigned) * group),
+           partials_dev(sizeof(double) * C_MAX * static_cast<size_t>(group) * blocks_cap);
+    PBK_CUDA(cudaMemsetAsync(counters_dev.as(), 0, sizeof(unsigned) * group, stream));
+
+    for (int c0 = 0; c0 < count; c0 += group) {
+        int const nc = std::min(group, count - c0);
         std::vector<Cone> cones(nc);
-        {   // host: the balls of this chunk, one thread per site
+        {   // host: the balls of this group, one thread per site (overlaps the device work of the previous group)
             std::vector<std::thread> pool;
-            int const nt = std::min<int>(static_cast<int>(marks.size()), nc);
+            int const nt = std::min(nthreads, nc);
             for (int t = 0; t < nt; ++t) {
                 pool.emplace_back([&, t] {
                     for (int j = t; j < nc; j += nt) {
-                        int32_t const site = target.src[first + c0 + j];
                         if (first + c0 + j == 0) cones[j] = first_cone;
-                        else cones[j] = bfs_cone(site, depth, marks[t]);
+                        else cones[j] = bfs_cone(target.src[first + c0 + j], depth, marks[t]);
                     }
                 });
             }
             for (auto& th : pool) th.join();
         }
+        // pooled buffers of the group
+        std::vector<int64_t> ell_off(nc + 1, 0), vec_off(nc + 1, 0);
+        std::vector<int64_t> pitches(nc), rows_all(nc);
+        int64_t max_queue = 0;
+        for (int j = 0; j < nc; ++j) {
+            rows_all[j] = cones[j].complete_rows();
+            pitches[j] = (rows_all[j] + 31) / 32 * 32;
+            ell_off[j + 1] = ell_off[j] + static_cast<int64_t>(kell) * pitches[j];
+            int64_t const nloc = static_cast<int64_t>(cones[j].queue.size());
+            vec_off[j + 1] = vec_off[j] + 2 * ((nloc + 31) / 32 * 32);
+            max_queue = std::max(max_queue, nloc);
+        }
+        // 25 % headroom: later groups (other ball sizes) should not force a re-allocation, which would wait for the device
+        auto ensure_room = [](DevBuf& b, size_t bytes) { if (bytes > b.bytes()) b.ensure(bytes + bytes / 4); };
+        ensure_room(cone_val, static_cast<size_t>(ell_off[nc]) * s);
+        ensure_room(cone_col, static_cast<size_t>(ell_off[nc]) * sizeof(int32_t));
+        ensure_room(vec_a, static_cast<size_t>(vec_off[nc]) * s);
+        ensure_room(cone_queue, sizeof(int32_t) * static_cast<size_t>(max_queue));
+        std::vector<ConeSlot> slots(nc);
+        std::vector<int32_t> rows_table(static_cast<size_t>(nc) * (steps + 1), 0);
+        std::vector<int64_t> max_rows(steps + 1, 0);
+        int64_t max_nvec = 0;
         for (int j = 0; j < nc; ++j) {
             Cone const& cone = cones[j];
             int64_t const nloc = static_cast<int64_t>(cone.queue.size());
-            int64_t const rows = cone.complete_rows();
-            int64_t const pitch = (rows + 31) / 32 * 32;
-            cone_queue.ensure(sizeof(int32_t) * nloc);
-            cone_val.ensure(static_cast<size_t>(kell) * pitch * s);
-            cone_col.ensure(static_cast<size_t>(kell) * pitch * sizeof(int32_t));
+            char* const val_j = cone_val.as<char>() + static_cast<size_t>(ell_off[j]) * s;
+            int32_t* const col_j = cone_col.as<int32_t>() + ell_off[j];
             PBK_CUDA(cudaMemcpyAsync(cone_queue.as(), cone.queue.data(), sizeof(int32_t) * nloc, cudaMemcpyHostToDevice, stream));
             stats.h2d_bytes += static_cast<int64_t>(sizeof(int32_t) * nloc);
             PBK_CUDA(launch_cone_mark(cone_queue.as<int32_t>(), nloc, perm, cone_gmap.as<int32_t>(), true, stream));
-            PBK_CUDA(launch_cone_extract(dtype, hn.ell, cone_queue.as<int32_t>(), perm, cone_gmap.as<int32_t>(), rows, cone_val.as(),
-                                         cone_col.as<int32_t>(), pitch, stream));
+            PBK_CUDA(launch_cone_extract(dtype, hn.ell, cone_queue.as<int32_t>(), perm, cone_gmap.as<int32_t>(), rows_all[j], val_j, col_j, pitches[j], stream));
             PBK_CUDA(launch_cone_mark(cone_queue.as<int32_t>(), nloc, perm, cone_gmap.as<int32_t>(), false, stream));
             launches += 3;
-
-            DeviceHamiltonian hc;   // a view: the buffers stay with the engine
-            hc.ell = EllDev{cone_val.as(), cone_col.as<int32_t>(), rows, pitch, kell};
-            hc.map = cone.map();
-            hc.idx = Indices{{0}, {0}};
-            hc.sliced = true;
-            hc.vec_rows = nloc;
-            hc.valid = true;
-            size_t const vbytes = static_cast<size_t>(nloc) * s;
-            vec_a.ensure(vbytes);
-            vec_b.ensure(vbytes);
-            idx_buf.ensure(sizeof(int32_t));
-            PBK_CUDA(cudaMemsetAsync(idx_buf.as(), 0, sizeof(int32_t), stream));   // the source is position 0 of its own ball
-            PBK_CUDA(launch_unit_starter(dtype, vec_a.as(), nloc, 1, idx_buf.as<int32_t>(), 1, stream));
-            launches += 1;
-            run_diagonal(hc, 1, M, true);
-            PBK_CUDA(cudaMemcpyAsync(cone_table.as<cd>() + static_cast<size_t>(c0 + j) * M, mom.as(), sizeof(cd) * M, cudaMemcpyDeviceToDevice, stream));
-            opt_rows += half_rows(hc.map);
-            full = full || hc.map.uses_full_system(M);
-            ++stats.num_batches;
-            progress(1, nidx);
+            SliceMap const map = cone.map();
+            int32_t* rt = rows_table.data() + static_cast<size_t>(j) * (steps + 1);
+            rt[1] = map.data[std::min(map.last_index(), 1)];
+            for (int k = 2; k <= steps; ++k) rt[k] = static_cast<int32_t>(map.optimal_size(k, M));
+            for (int k = 1; k <= steps; ++k) max_rows[k] = std::max<int64_t>(max_rows[k], rt[k]);
+            max_nvec = std::max(max_nvec, nloc);
+            ConeSlot& sl = slots[j];
+            sl.val = val_j; sl.col = col_j; sl.pitch = pitches[j];
+            sl.buf[0] = vec_a.as<char>() + static_cast<size_t>(vec_off[j]) * s;
+            sl.buf[1] = vec_a.as<char>() + static_cast<size_t>(vec_off[j] + (nloc + 31) / 32 * 32) * s;
+            sl.nvec = nloc;
+            sl.rows = rows_dev.as<int32_t>() + static_cast<size_t>(j) * (steps + 1);
+            sl.mom = cone_table.as<double>() + 2 * static_cast<size_t>(c0 + j) * M;
+            sl.m01 = m01_dev.as<double>() + 3 * j;
+            opt_rows += half_rows(map);
+            full = full || map.uses_full_system(M);
         }
+        PBK_CUDA(cudaMemcpyAsync(slots_dev.as(), slots.data(), sizeof(ConeSlot) * nc, cudaMemcpyHostToDevice, stream));
+        PBK_CUDA(cudaMemcpyAsync(rows_dev.as(), rows_table.data(), sizeof(int32_t) * rows_table.size(), cudaMemcpyHostToDevice, stream));
+        if (c0 == 0) PBK_CUDA(cudaEventRecord(ev2, stream));
+        PBK_CUDA(launch_cone_group_start(dtype, slots_dev.as<ConeSlot>(), nc, max_nvec, stream));
+        ++launches;
+        for (int k = 1; k <= steps; ++k) {
+            PBK_CUDA(launch_cone_group_step(dtype, slots_dev.as<ConeSlot>(), nc, k, kell, M, max_rows[k], partials_dev.as<double>(),
+                                            counters_dev.as<unsigned>(), blocks_cap, stream));
+            ++launches;
+            ++stats.step_launches;
+            for (int j = 0; j < nc; ++j) {
+                int64_t const r = rows_table[static_cast<size_t>(j) * (steps + 1) + k];
+                stats.step_bytes += static_cast<double>(r) * (kell * (s + 4.0) + (k == 1 ? 2.0 : 3.0) * s);
+            }
+        }
+        // no synchronisation here: the host walks the balls of the next group while the device advances this one
+        // (the pageable uploads above were staged when they were issued)
+        stats.num_batches += 1;
+        progress(nc, nidx);
+    }
+    if (count > 0) {
+        PBK_CUDA(cudaEventRecord(ev3, stream));
+        PBK_CUDA(cudaEventSynchronize(ev3));
+        float ms = 0;
+        PBK_CUDA(cudaEventElapsedTime(&ms, ev2, ev3));
+        stats.step_ms += ms;   // first step of the first group .. last step of the last group (extraction of later groups included)
     }
     if (count > 0) {
         std::vector<cd> host(static_cast<size_t>(count) * M);
@@ -1486,14 +1602,19 @@ void Engine::calc_ldos(const double* energy, int ne, double broadening, const in
 
 void Engine::calc_greens(int row, const int32_t* cols, int ncols, const double* energy, int ne, double broadening, cd* out) {
     double const t0 = now_seconds();
+    bool const timing = std::getenv("PBK_TIMING") != nullptr;
     auto const s = scaling_factors();
     int const M = required_num_moments(broadening);
     std::vector<cd> m(static_cast<size_t>(M) * ncols);
+    double const t1 = now_seconds();
     moments_greens(M, row, cols, ncols, m.data());
+    double const t2 = now_seconds();
     auto const g = damping_coefficients(config.kernel, config.lambda_value, M);
     for (int i = 0; i < ncols; ++i) for (int k = 0; k < M; ++k) m[static_cast<size_t>(i) * M + k] *= g[k];
     greens_device(m.data(), M, ncols, energy, ne, s, out);
     last_total_seconds = now_seconds() - t0;
+    if (timing) std::fprintf(stderr, "[pbkpm] calc_greens: setup %.3f s, moments_greens %.3f s (hamiltonian %.3f, moments phase %.3f), reconstruction %.3f s\n",
+                             t1 - t0, t2 - t1, stats.hamiltonian_time, stats.moments_time, now_seconds() - t2);
 }
 
 void Engine::calc_conductivity(const float* left, const float* right, const double* mu, int nmu, double broadening,

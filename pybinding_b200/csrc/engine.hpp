@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 #include <cstdint>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -76,6 +77,7 @@ struct DeviceHamiltonian {
     bool reordered = false;        // rows are relabelled: reorder_map / perm are set
     bool sliced = false;           // BFS order from the source: `map` holds the light-cone slices
     int64_t tile = 0;              // ORDER_CLUSTER: rows per locality cluster (the step kernel's CTA tile), else 0
+    bool transient = false;        // rebuilt for every calculation (light-cone sub-systems): its launch sequence is not worth caching
     int64_t vec_rows = 0;          // length of a KPM vector on this layout (0: the system size); light-cone sub-systems are shorter
     std::vector<int32_t> order_queue;  // device row -> original (ORDER_CLUSTER only)
     Indices original_idx, idx;     // idx: positions in the device ordering
@@ -231,6 +233,14 @@ private:
     std::unique_ptr<NcclApi> nccl;
     void* comm = nullptr;
     int world = 1, rank = 0;
+
+    // ---- CUDA graphs of launch-bound recursions (small systems): the whole sequence of step launches of one
+    //      diagonal run is captured once and replayed, keyed by every baked-in pointer and row count ----
+    struct RecursionGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0, step_launches = 0, bulk_launches = 0; double step_bytes = 0; };
+    std::map<std::vector<int64_t>, RecursionGraph> graph_cache;
+    int graph_mode = 1;
+    double graph_max_bytes = 64e6;   // vector block size up to which a recursion counts as launch-bound
+    void clear_graphs();
 
     pbk_stats stats{};
     double last_total_seconds = 0;

@@ -419,6 +419,55 @@ __global__ void cone_extract_kernel(const T* __restrict__ val, const int32_t* __
     }
 }
 
+/// One Chebyshev step of the diagonal recursion for a GROUP of independent light-cone sub-systems (one unit vector
+/// each): blockIdx.y selects the sub-system, blockIdx.x strides over its rows of this step.  Step k reads r_{k-1} from
+/// buf[(k-1)&1], overwrites r_{k-2} in buf[k&1] with r_k, and the last block of each sub-system writes its two moments
+/// (same arithmetic and reductions as `cheb_step` with R = 1).  k == 1 is the initial step r_1 = H~ r_0 / 2.
+template<class T>
+__global__ void __launch_bounds__(256) cone_group_step_kernel(const ConeSlot* __restrict__ slots, int k, int kell, int M,
+                                                              double* partials, unsigned* counters) {
+    constexpr int C = ST<T>::C;
+    ConeSlot const sl = slots[blockIdx.y];
+    const T* __restrict__ val = static_cast<const T*>(sl.val);
+    const int32_t* __restrict__ col = sl.col;
+    const T* __restrict__ x = static_cast<const T*>(sl.buf[(k - 1) & 1]);
+    T* __restrict__ y = static_cast<T*>(sl.buf[k & 1]);
+    int64_t const nrows = sl.rows[k];
+    bool const init = k == 1;
+    double acc[C];
+#pragma unroll
+    for (int q = 0; q < C; ++q) acc[q] = 0.0;
+    for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < nrows; row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        T r = init ? zero_(T{}) : neg_(y[row]);
+        for (int s = 0; s < kell; ++s) {
+            int32_t const c = __ldg(col + s * sl.pitch + row);
+            T const v = ldg_scalar(val + s * sl.pitch + row);
+            r = fma_(v, ldg_scalar(x + c), r);
+        }
+        if (init) r = scale_(r, 0.5);
+        sums_(acc, ldg_scalar(x + row), r);
+        y[row] = r;
+    }
+    StepDev fin{};
+    fin.R = 1; fin.cpr = 1; fin.rpb = 256;
+    fin.partials = partials + static_cast<int64_t>(blockIdx.y) * gridDim.x * C;
+    fin.counter = counters + blockIdx.y;
+    fin.mom = sl.mom; fin.m01 = sl.m01; fin.M = M; fin.n = k; fin.fin = init ? FIN_INIT : FIN_STEP;
+    finish_sums<C, C, 256>(fin, acc, 0, static_cast<int>(threadIdx.x));
+}
+
+/// buf0 = unit vector at position 0, buf1 = 0 for every sub-system of a group
+template<class T>
+__global__ void cone_group_start_kernel(const ConeSlot* __restrict__ slots) {
+    ConeSlot const sl = slots[blockIdx.y];
+    T* b0 = static_cast<T*>(sl.buf[0]);
+    T* b1 = static_cast<T*>(sl.buf[1]);
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < sl.nvec; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        b0[i] = i == 0 ? from_c128<T>(1.0, 0.0) : zero_(T{});
+        b1[i] = zero_(T{});
+    }
+}
+
 // ---- Lanczos -----------------------------------------------------------------------------------
 template<class T> __device__ __forceinline__ T axpy_(double a, T x, T y);  // y - a*x
 template<> __device__ __forceinline__ float axpy_(double a, float x, float y) { return y - static_cast<float>(a) * x; }
@@ -499,6 +548,25 @@ cudaError_t launch_scatter_block(int dtype, const double* src_c128, int64_t n, i
 cudaError_t launch_extract_lane(int dtype, const void* v, int64_t n, int R, int lane, const int32_t* perm_dev, double* out_c128, cudaStream_t s) {
     int const grid = static_cast<int>((n + 255) / 256);
     PBK_DISPATCH(dtype, (extract_lane_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(v), n, R, lane, perm_dev, out_c128)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cone_group_start(int dtype, const ConeSlot* slots_dev, int nslots, int64_t max_nvec, cudaStream_t s) {
+    int gx = static_cast<int>((max_nvec + 255) / 256);
+    if (gx > 512) gx = 512;
+    if (gx < 1) gx = 1;
+    dim3 const grid(gx, nslots);
+    PBK_DISPATCH(dtype, (cone_group_start_kernel<T><<<grid, 256, 0, s>>>(slots_dev)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cone_group_step(int dtype, const ConeSlot* slots_dev, int nslots, int k, int kell, int M, int64_t max_rows,
+                                   double* partials, unsigned* counters, int blocks_per_slot_cap, cudaStream_t s) {
+    int64_t need = (max_rows + 255) / 256;
+    if (need < 1) need = 1;
+    int const gx = static_cast<int>(need < blocks_per_slot_cap ? need : blocks_per_slot_cap);
+    dim3 const grid(gx, nslots);
+    PBK_DISPATCH(dtype, (cone_group_step_kernel<T><<<grid, 256, 0, s>>>(slots_dev, k, kell, M, partials, counters)));
     return cudaGetLastError();
 }
 

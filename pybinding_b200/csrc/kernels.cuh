@@ -115,6 +115,22 @@ cudaError_t launch_cone_mark(const int32_t* queue_dev, int64_t count, const int3
 cudaError_t launch_cone_extract(int dtype, EllDev const& h, const int32_t* queue_dev, const int32_t* perm_dev, const int32_t* gmap,
                                 int64_t rows, void* out_val, int32_t* out_col, int64_t out_pitch, cudaStream_t s);
 
+/// One light-cone sub-system of a group (device-resident table read by cone_group_step_kernel)
+struct ConeSlot {
+    const void* val; const int32_t* col; int64_t pitch;   // sub-ELL (slot-major)
+    void* buf[2];                                          // r_even / r_odd
+    int64_t nvec;                                          // vector length (sites of the ball)
+    const int32_t* rows;                                   // rows[k]: rows processed at step k, k = 1 .. M/2
+    double* mom;                                           // c128 [M]
+    double* m01;                                           // [3]
+};
+/// unit starters of a group: buf[0] = e_0, buf[1] = 0
+cudaError_t launch_cone_group_start(int dtype, const ConeSlot* slots_dev, int nslots, int64_t max_nvec, cudaStream_t s);
+/// step k (1 = initial step) for all sub-systems of a group in one launch; partials: [nslots][blocks][C] doubles,
+/// counters: nslots zeroed unsigned
+cudaError_t launch_cone_group_step(int dtype, const ConeSlot* slots_dev, int nslots, int k, int kell, int M, int64_t max_rows,
+                                   double* partials, unsigned* counters, int blocks_per_slot_cap, cudaStream_t s);
+
 // ---- random starters (mt19937.cu) ------------------------------------------------------------
 constexpr int MT_N = 624;
 /// state_dev: 624 words + 1 position word.  Seeds std::mt19937's default state (seed 5489, position 624).

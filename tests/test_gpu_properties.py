@@ -24,7 +24,8 @@ pytestmark = pytest.mark.gpu
 TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.complex64): 1e-5,
        np.dtype(np.float64): 1e-11, np.dtype(np.complex128): 1e-11}
 KNOBS = ("PBK_BULK", "PBK_XS", "PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL",
-         "PBK_PAIR", "PBK_PAIR_STAGES", "PBK_PAIR_MINB", "PBK_PAIR_R", "PBK_CONE")
+         "PBK_PAIR", "PBK_PAIR_STAGES", "PBK_PAIR_MINB", "PBK_PAIR_R", "PBK_CONE",
+         "PBK_GRAPH", "PBK_GRAPH_MAX_MB")
 
 
 @contextmanager
@@ -201,29 +202,33 @@ def test_ldos_equals_dos_of_unit_vectors_and_sum_rule():
 
 
 def test_spread_ldos_sites_use_full_system_layout_and_match_single_site_runs():
-    """LDOS at sites spread over the sample (core.ldos(indices), cppcore/src/kpm/Core.cpp:58-72): the union of the light
-    cones is the whole system, so the engine advances the unit vectors on the locality layout with the staged kernel;
-    each column must equal the light-cone-sliced single-site run."""
+    """LDOS at sites spread over the sample (core.ldos(indices), cppcore/src/kpm/Core.cpp:58-72) without the light-cone
+    sub-systems (PBK_CONE=0): the union of the light cones is the whole system, so the engine advances the unit vectors
+    on the locality layout with the staged kernel; each column must equal the light-cone-sliced single-site run."""
     model = pb.graphene_rectangle(30.0, dtype=np.complex128, magnetic_field=200.0, disorder=0.3)
-    kpm = pb.kpm(model, energy_range=(-9.2, 9.2), silent=True)
     fn = model.system.find_nearest
     sites = [fn([x, y]) for x in (-12, -4, 4, 12) for y in (-10, 0, 10)]
     M = 258
-    batch = kpm.impl.moments_ldos(M, sites)
-    s = kpm.stats
-    assert s.bulk_launches > 0 and s.opt_nnz == s.nnz          # full system, staged kernel
-    single = pb.kpm(model, energy_range=(-9.2, 9.2), silent=True)
-    for j, site in enumerate(sites):
-        one = single.impl.moments_ldos(M, [site])[:, 0]
-        assert np.abs(batch[:, j] - one).max() / np.abs(one).max() < 1e-11
-    assert single.stats.bulk_launches == 0 and single.stats.opt_nnz < single.stats.nnz   # light-cone sliced
-    # neighbouring sites (one cell) keep the sliced layout
-    near = [fn([0, 0], "A"), fn([0, 0], "B")]
-    both = single.impl.moments_ldos(M, near)
-    assert single.stats.opt_nnz < single.stats.nnz
-    for j, site in enumerate(near):
-        one = kpm.impl.moments_ldos(M, [site])[:, 0]
-        assert np.abs(both[:, j] - one).max() / np.abs(one).max() < 1e-11
+    with knobs(PBK_CONE=0):
+        kpm = pb.kpm(model, energy_range=(-9.2, 9.2), silent=True)
+        batch = kpm.impl.moments_ldos(M, sites)
+        s = kpm.stats
+        assert s.bulk_launches > 0 and s.opt_nnz == s.nnz          # full system, staged kernel
+        single = pb.kpm(model, energy_range=(-9.2, 9.2), silent=True)
+        for j, site in enumerate(sites):
+            one = single.impl.moments_ldos(M, [site])[:, 0]
+            assert np.abs(batch[:, j] - one).max() / np.abs(one).max() < 1e-11
+        assert single.stats.bulk_launches == 0 and single.stats.opt_nnz < single.stats.nnz   # light-cone sliced
+        # neighbouring sites (one cell) keep the sliced layout
+        near = [fn([0, 0], "A"), fn([0, 0], "B")]
+        both = single.impl.moments_ldos(M, near)
+        assert single.stats.opt_nnz < single.stats.nnz
+        for j, site in enumerate(near):
+            one = kpm.impl.moments_ldos(M, [site])[:, 0]
+            assert np.abs(both[:, j] - one).max() / np.abs(one).max() < 1e-11
+    # default engine (light-cone sub-systems where they pay): same table
+    default = pb.kpm(model, energy_range=(-9.2, 9.2), silent=True).impl.moments_ldos(M, sites)
+    assert np.abs(default - batch).max() / np.abs(batch).max() < 1e-11
 
 
 def ldos_moments(model, energy_range, M, sites, **kw):
@@ -260,9 +265,37 @@ def test_cone_ldos_many_sites_of_a_large_system():
     sites = [fn([-60, 10]), fn([0, 0]), fn([99.9, -99.9]), fn([35, 70])]
     M = 130
     batch, s = ldos_moments(model, (-9, 9), M, sites)
-    assert s.num_batches == len(sites) and s.bulk_launches == 0 and s.batch == 1
+    assert s.num_batches == 1 and s.batch == len(sites) and s.bulk_launches == 0 and s.step_launches == M // 2   # one group
     assert s.opt_nnz < s.nnz / 50
     for j, site in enumerate(sites):
         one, s0 = ldos_moments(model, (-9, 9), M, [site], PBK_CONE=0)
         assert np.abs(batch[:, j] - one[:, 0]).max() / np.abs(one).max() < 1e-12
     assert np.all(batch[0].real == 0.5) and np.all(batch.imag == 0)
+
+
+def test_graph_replay_of_small_recursions_is_bit_identical():
+    """Launch-bound recursions (small systems) are captured once as a CUDA graph and replayed: same kernels, same
+    parameters, so the moments are bit-identical to plain launches, call after call, for DOS and LDOS"""
+    model = pb.graphene_rectangle(40.0, dtype=np.float32)     # configs[0]: 61 k sites
+    M = 1026
+    with knobs(PBK_GRAPH=0):
+        plain_kpm = pb.kpm(model, energy_range=(-8.5, 8.5), silent=True)
+        plain = plain_kpm.impl.moments_dos(M, 1)
+        assert plain_kpm.stats.graph_launches == 0
+        site = model.system.find_nearest([3, 4])
+        plain_ldos = pb.kpm(model, energy_range=(-8.5, 8.5), silent=True).impl.moments_greens(M, site, [site])
+    kpm = pb.kpm(model, energy_range=(-8.5, 8.5), silent=True)
+    for call in range(3):
+        mom = kpm.impl.moments_dos(M, 1)
+        s = kpm.stats
+        assert s.graph_launches == 1 and s.step_launches == M // 2 and s.kernel_launches > M // 2
+        assert np.array_equal(mom, plain), call
+    for call in range(2):   # light-cone sliced diagonal Green's function through the relabelled Hamiltonian
+        g = kpm.impl.moments_greens(M, site, [site])
+        assert kpm.stats.graph_launches == 1
+        assert np.array_equal(g, plain_ldos), call
+    big = pb.graphene_rectangle(60.0, dtype=np.complex64, magnetic_field=100.0)
+    with knobs(PBK_GRAPH_MAX_MB=1):
+        k2 = pb.kpm(big, energy_range=(-8.5, 8.5), silent=True)
+        k2.impl.moments_dos(66, 16)
+        assert k2.stats.graph_launches == 0      # 137 k sites x 16 vectors x 8 bytes = 17.6 MB > 1 MB: plain launches
