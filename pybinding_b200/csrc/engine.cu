@@ -43,6 +43,18 @@ void DevBuf::release() {
     if (ptr) { cudaFree(ptr); ptr = nullptr; size = 0; }
 }
 
+void* PinnedBuf::ensure(size_t bytes) {
+    if (bytes > size) {
+        release();
+        if (cudaMallocHost(&ptr, bytes) != cudaSuccess) { cudaGetLastError(); ptr = nullptr; size = 0; return nullptr; }  // caller falls back to pageable memory
+        size = bytes;
+    }
+    return ptr;
+}
+void PinnedBuf::release() {
+    if (ptr) { cudaFreeHost(ptr); ptr = nullptr; size = 0; }
+}
+
 static double now_seconds() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -145,6 +157,7 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     step_prefetch_mask = static_cast<int>(env_int("PBK_PFMASK", 0));
     bulk_stages = static_cast<int>(env_int("PBK_BULK", 4));
     bulk_xstage = env_int("PBK_XS", 1) != 0;
+    identity_order = env_int("PBK_IDENTITY_ORDER", 0) != 0;
     cone_mode = static_cast<int>(env_int("PBK_CONE", 1));
     graph_mode = static_cast<int>(env_int("PBK_GRAPH", 1));
     graph_max_bytes = 1e6 * static_cast<double>(env_int("PBK_GRAPH_MAX_MB", 64));
@@ -183,9 +196,24 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
     dtype = dt;
     n = n_;
     int64_t const nnz = indptr[n];
-    h_indptr.assign(indptr, indptr + n + 1);
-    h_indices.assign(indices, indices + nnz);
-    h_data.assign(static_cast<const char*>(data), static_cast<const char*>(data) + nnz * dtype_size(dt));
+    // the locality ordering of the full-system layout only needs the sparsity pattern: it runs on the caller's arrays in
+    // a second thread while this one copies them (parallel first touch)
+    cluster_queue.clear(); cluster_rmap.clear(); cluster_tile = 0;
+    std::thread ordering;
+    if (locality_tile > 0 && !identity_order) {
+        cluster_tile = locality_tile;
+        ordering = std::thread([this, n_, indptr, indices] { cluster_order(n_, indptr, indices, cluster_tile, cluster_queue, cluster_rmap); });
+    }
+    h_indptr.resize_uninit(static_cast<size_t>(n) + 1);
+    h_indices.resize_uninit(static_cast<size_t>(nnz));
+    h_data.resize_uninit(static_cast<size_t>(nnz) * dtype_size(dt));
+    parallel_rows(n + 1, [&](int64_t b, int64_t e) { std::memcpy(h_indptr.data() + b, indptr + b, sizeof(int32_t) * static_cast<size_t>(e - b)); });
+    parallel_rows(nnz, [&](int64_t b, int64_t e) {
+        std::memcpy(h_indices.data() + b, indices + b, sizeof(int32_t) * static_cast<size_t>(e - b));
+        size_t const sz = dtype_size(dt);
+        std::memcpy(h_data.data() + b * sz, static_cast<const char*>(data) + b * sz, sz * static_cast<size_t>(e - b));
+    });
+    if (ordering.joinable()) ordering.join();
     has_h = true;
     clear_graphs();
     natural = DeviceHamiltonian();
@@ -216,13 +244,17 @@ template<class R> struct real_of<std::complex<R>> { using type = R; };
 struct HostEll {
     int k = 0;
     int64_t pitch = 0;
-    std::vector<char> val;
-    std::vector<int32_t> col;
+    char* val = nullptr;        // k * pitch scalars
+    int32_t* col = nullptr;     // k * pitch
+    size_t val_bytes = 0, col_count = 0;
+    RawVec<char> val_own;       // storage when no staging buffer was supplied
+    RawVec<int32_t> col_own;
 };
 
 template<class T>
 HostEll build_ell_host(int64_t n, const int32_t* indptr, const int32_t* indices, const T* data, bool scaled, Scale s,
-                       const int32_t* queue /*new->old or null*/, const int32_t* rmap /*old->new or null*/) {
+                       const int32_t* queue /*new->old or null*/, const int32_t* rmap /*old->new or null*/,
+                       PinnedBuf* stage_val = nullptr, PinnedBuf* stage_col = nullptr) {
     using R = typename real_of<T>::type;
     R const sa = static_cast<R>(s.a), sb = scaled ? static_cast<R>(s.b) : R{0};
     R const f = scaled ? R{2} / sa : R{1};
@@ -251,10 +283,15 @@ HostEll build_ell_host(int64_t n, const int32_t* indptr, const int32_t* indices,
     HostEll ell;
     ell.k = std::max(kmax, 1);
     ell.pitch = (n + 31) / 32 * 32;
-    ell.val.assign(static_cast<size_t>(ell.k) * ell.pitch * sizeof(T), 0);
-    ell.col.assign(static_cast<size_t>(ell.k) * ell.pitch, 0);
-    T* val = reinterpret_cast<T*>(ell.val.data());
-    int32_t* col = ell.col.data();
+    ell.val_bytes = static_cast<size_t>(ell.k) * ell.pitch * sizeof(T);
+    ell.col_count = static_cast<size_t>(ell.k) * ell.pitch;
+    // every element is written below (entries, padding, tail rows): no zero-fill pass; page-locked staging when offered
+    ell.val = stage_val ? static_cast<char*>(stage_val->ensure(ell.val_bytes)) : nullptr;
+    ell.col = stage_col ? static_cast<int32_t*>(stage_col->ensure(ell.col_count * sizeof(int32_t))) : nullptr;
+    if (!ell.val) { ell.val_own.resize_uninit(ell.val_bytes); ell.val = ell.val_own.data(); }
+    if (!ell.col) { ell.col_own.resize_uninit(ell.col_count); ell.col = ell.col_own.data(); }
+    T* val = reinterpret_cast<T*>(ell.val);
+    int32_t* col = ell.col;
     int const k = ell.k;
     int64_t const pitch = ell.pitch;
 
@@ -281,11 +318,11 @@ HostEll build_ell_host(int64_t n, const int32_t* indptr, const int32_t* indices,
             std::sort(buf.begin(), buf.end(), [](auto const& l, auto const& r) { return l.first < r.first; });
             int sidx = 0;
             for (auto const& en : buf) { val[sidx * pitch + new_row] = en.second; col[sidx * pitch + new_row] = en.first; ++sidx; }
-            for (; sidx < k; ++sidx) col[sidx * pitch + new_row] = static_cast<int32_t>(new_row);
+            for (; sidx < k; ++sidx) { val[sidx * pitch + new_row] = T{0}; col[sidx * pitch + new_row] = static_cast<int32_t>(new_row); }
         }
         (void)k;
     });
-    for (int sidx = 0; sidx < k; ++sidx) for (int64_t r = n; r < pitch; ++r) col[sidx * pitch + r] = 0;
+    for (int sidx = 0; sidx < k; ++sidx) for (int64_t r = n; r < pitch; ++r) { val[sidx * pitch + r] = T{0}; col[sidx * pitch + r] = 0; }
     return ell;
 }
 
@@ -328,12 +365,18 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
         bool full = false;
         while (head < queue.size() && !full) {
             int32_t const row = queue[head];
-            for (int p = indptr[row]; p < indptr[row + 1]; ++p) {
+            if (head + 4 < queue.size()) {   // the queue is the access pattern: pull the adjacency of a later row into cache
+                int32_t const ahead = queue[head + 4];
+                __builtin_prefetch(indices + indptr[ahead]);
+            }
+            int const pend = indptr[row + 1];
+            for (int p = indptr[row]; p < pend; ++p) {
                 int32_t const c = indices[p];
                 if (rmap[c] >= 0) continue;
                 if (queue.size() >= limit) { full = true; break; }
                 rmap[c] = static_cast<int32_t>(queue.size());
                 queue.push_back(c);
+                __builtin_prefetch(indptr + c);
             }
             if (!full) ++head;
         }
@@ -449,7 +492,17 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
 
     std::vector<int32_t> queue;
     if (order == ORDER_CLUSTER) {
-        cluster_order(n, h_indptr.data(), h_indices.data(), locality_tile, queue, dh.reorder_map);
+        if (identity_order) {   // PBK_IDENTITY_ORDER=1: the caller's site order, cut into tiles of consecutive rows (staged kernel applies)
+            queue.resize(n);
+            for (int64_t i = 0; i < n; ++i) queue[i] = static_cast<int32_t>(i);
+            dh.reorder_map = queue;
+        } else if (cluster_tile == locality_tile && static_cast<int64_t>(cluster_queue.size()) == n) {   // computed by set_hamiltonian
+            queue = std::move(cluster_queue);
+            dh.reorder_map = std::move(cluster_rmap);
+            cluster_queue.clear(); cluster_rmap.clear(); cluster_tile = 0;
+        } else {
+            cluster_order(n, h_indptr.data(), h_indices.data(), locality_tile, queue, dh.reorder_map);
+        }
         for (int32_t i : target.src) dh.idx.src.push_back(dh.reorder_map[i]);
         for (int32_t i : target.dest) dh.idx.dest.push_back(dh.reorder_map[i]);
         dh.map.data = {static_cast<int32_t>(n)};
@@ -480,17 +533,20 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
     const int32_t* q = reorder ? queue.data() : nullptr;
     const int32_t* rm = reorder ? dh.reorder_map.data() : nullptr;
     if (order == ORDER_CLUSTER) dh.order_queue = queue;  // operators of the same calculation are laid out alike
+    // the full-system layout (the big, long-lived one) is staged in the context's page-locked buffers
+    PinnedBuf* const sv = (&dh == &natural) ? &stage_val : nullptr;
+    PinnedBuf* const sc = (&dh == &natural) ? &stage_col : nullptr;
     switch (dtype) {
-        case F32: ell = build_ell_host<float>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const float*>(h_data.data()), scaled, s, q, rm); break;
-        case C64: ell = build_ell_host<cf>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cf*>(h_data.data()), scaled, s, q, rm); break;
-        case F64: ell = build_ell_host<double>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const double*>(h_data.data()), scaled, s, q, rm); break;
-        default: ell = build_ell_host<cd>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cd*>(h_data.data()), scaled, s, q, rm); break;
+        case F32: ell = build_ell_host<float>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const float*>(h_data.data()), scaled, s, q, rm, sv, sc); break;
+        case C64: ell = build_ell_host<cf>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cf*>(h_data.data()), scaled, s, q, rm, sv, sc); break;
+        case F64: ell = build_ell_host<double>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const double*>(h_data.data()), scaled, s, q, rm, sv, sc); break;
+        default: ell = build_ell_host<cd>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cd*>(h_data.data()), scaled, s, q, rm, sv, sc); break;
     }
-    dh.val.alloc(ell.val.size());
-    dh.col.alloc(ell.col.size() * sizeof(int32_t));
-    PBK_CUDA(cudaMemcpyAsync(dh.val.as(), ell.val.data(), ell.val.size(), cudaMemcpyHostToDevice, stream));
-    PBK_CUDA(cudaMemcpyAsync(dh.col.as(), ell.col.data(), ell.col.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-    stats.h2d_bytes += static_cast<int64_t>(ell.val.size() + ell.col.size() * sizeof(int32_t));
+    dh.val.alloc(ell.val_bytes);
+    dh.col.alloc(ell.col_count * sizeof(int32_t));
+    PBK_CUDA(cudaMemcpyAsync(dh.val.as(), ell.val, ell.val_bytes, cudaMemcpyHostToDevice, stream));
+    PBK_CUDA(cudaMemcpyAsync(dh.col.as(), ell.col, ell.col_count * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    stats.h2d_bytes += static_cast<int64_t>(ell.val_bytes + ell.col_count * sizeof(int32_t));
     if (reorder) {
         dh.perm.alloc(sizeof(int32_t) * n);
         PBK_CUDA(cudaMemcpyAsync(dh.perm.as(), dh.reorder_map.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream));
@@ -504,7 +560,7 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
     if (order == ORDER_CLUSTER && bulk_stages >= 2) {  // row-major records for the bulk-copy staged step kernel
         dh.packed.alloc(packed_ell_bytes(dtype, dh.ell));
         PBK_CUDA(launch_pack_ell(dtype, dh.ell, dh.packed.as(), stream));
-        if (pair_mode) build_pair_metadata(dh, ell.col.data(), ell.pitch, ell.k);
+        if (pair_mode) build_pair_metadata(dh, ell.col, ell.pitch, ell.k);
     }
     PBK_CUDA(cudaStreamSynchronize(stream));
     dh.original_idx = target;
@@ -566,11 +622,11 @@ void Engine::upload_operator(DeviceHamiltonian& dh, const float* pos, DeviceHami
     }
     dh = DeviceHamiltonian();
     dh.tile = like.tile;
-    dh.val.alloc(ell.val.size());
-    dh.col.alloc(ell.col.size() * sizeof(int32_t));
-    PBK_CUDA(cudaMemcpy(dh.val.as(), ell.val.data(), ell.val.size(), cudaMemcpyHostToDevice));
-    PBK_CUDA(cudaMemcpy(dh.col.as(), ell.col.data(), ell.col.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    stats.h2d_bytes += static_cast<int64_t>(ell.val.size() + ell.col.size() * sizeof(int32_t));
+    dh.val.alloc(ell.val_bytes);
+    dh.col.alloc(ell.col_count * sizeof(int32_t));
+    PBK_CUDA(cudaMemcpy(dh.val.as(), ell.val, ell.val_bytes, cudaMemcpyHostToDevice));
+    PBK_CUDA(cudaMemcpy(dh.col.as(), ell.col, ell.col_count * sizeof(int32_t), cudaMemcpyHostToDevice));
+    stats.h2d_bytes += static_cast<int64_t>(ell.val_bytes + ell.col_count * sizeof(int32_t));
     dh.ell = EllDev{dh.val.as(), dh.col.as<int32_t>(), n, ell.pitch, ell.k};
     dh.map.data = {static_cast<int32_t>(n)};
     dh.valid = true;
@@ -594,11 +650,11 @@ void Engine::upload_csr_operator(DeviceHamiltonian& dh, int64_t rows, const int3
     }
     dh = DeviceHamiltonian();
     dh.tile = like.tile;
-    dh.val.alloc(ell.val.size());
-    dh.col.alloc(ell.col.size() * sizeof(int32_t));
-    PBK_CUDA(cudaMemcpy(dh.val.as(), ell.val.data(), ell.val.size(), cudaMemcpyHostToDevice));
-    PBK_CUDA(cudaMemcpy(dh.col.as(), ell.col.data(), ell.col.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    stats.h2d_bytes += static_cast<int64_t>(ell.val.size() + ell.col.size() * sizeof(int32_t));
+    dh.val.alloc(ell.val_bytes);
+    dh.col.alloc(ell.col_count * sizeof(int32_t));
+    PBK_CUDA(cudaMemcpy(dh.val.as(), ell.val, ell.val_bytes, cudaMemcpyHostToDevice));
+    PBK_CUDA(cudaMemcpy(dh.col.as(), ell.col, ell.col_count * sizeof(int32_t), cudaMemcpyHostToDevice));
+    stats.h2d_bytes += static_cast<int64_t>(ell.val_bytes + ell.col_count * sizeof(int32_t));
     dh.ell = EllDev{dh.val.as(), dh.col.as<int32_t>(), rows, ell.pitch, ell.k};
     dh.map.data = {static_cast<int32_t>(rows)};
     dh.valid = true;

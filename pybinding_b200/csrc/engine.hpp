@@ -46,6 +46,35 @@ private:
     size_t size = 0;
 };
 
+/// Host array without value-initialisation: large buffers are first touched by the (parallel) code that fills them
+template<class T> class RawVec {
+public:
+    void resize_uninit(size_t count) { if (count != n) { p.reset(count ? new T[count] : nullptr); n = count; } }
+    T* data() { return p.get(); }
+    const T* data() const { return p.get(); }
+    size_t size() const { return n; }
+    T& operator[](size_t i) { return p[i]; }
+    T const& operator[](size_t i) const { return p[i]; }
+private:
+    std::unique_ptr<T[]> p;
+    size_t n = 0;
+};
+
+/// Page-locked host staging buffer, kept by the context and grown on demand: uploads run at the link rate and the
+/// pinning cost is paid once per context, not once per Hamiltonian
+class PinnedBuf {
+public:
+    PinnedBuf() = default;
+    PinnedBuf(PinnedBuf const&) = delete;
+    PinnedBuf& operator=(PinnedBuf const&) = delete;
+    ~PinnedBuf() { release(); }
+    void* ensure(size_t bytes);
+    void release();
+private:
+    void* ptr = nullptr;
+    size_t size = 0;
+};
+
 /// kpm::Scale (cppcore/include/kpm/Bounds.hpp:11-33) including its single-precision constants
 struct Scale {
     double a = 0, b = 0;
@@ -204,9 +233,13 @@ private:
     // ---- host copy of the Hamiltonian (original order, unscaled) ----
     int dtype = -1;
     int64_t n = 0;
-    std::vector<int32_t> h_indptr, h_indices;
-    std::vector<char> h_data;
+    RawVec<int32_t> h_indptr, h_indices;
+    RawVec<char> h_data;
     bool has_h = false;
+    // locality ordering of the full-system layout, computed while set_hamiltonian copies the arrays
+    std::vector<int32_t> cluster_queue, cluster_rmap;
+    int64_t cluster_tile = 0;
+    PinnedBuf stage_val, stage_col;   // ELL staging of the full-system layout
 
     // ---- bounds ----
     bool have_bounds = false;
@@ -223,6 +256,7 @@ private:
     DevBuf vec_c, vec_d;         // second vector pair of the two-step kernel
     DevBuf cone_val, cone_col, cone_queue, cone_gmap, cone_table;   // light-cone sub-system of the site being processed
     int64_t cone_gmap_rows = 0;  // cone_gmap holds -1 for this many rows
+    bool identity_order = false; // PBK_IDENTITY_ORDER=1: tiles of consecutive rows in the caller's order instead of locality clusters
     int cone_mode = 1;           // PBK_CONE=0: the previous host-side full BFS relabelling for LDOS
     DevBuf vec_a, vec_b, vec_t, raw, mom, m01, acc, partials, counter, scratch, mt_state, mt_states, idx_buf;
     static constexpr int MT_MAX_SEGMENTS = 2048;
