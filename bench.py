@@ -175,10 +175,33 @@ def run_reference(args, w):
                config=dict(workload=w["text"], note="CPU sample extrapolates linearly in moments and vectors"),
                cpu_baseline=base,
                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(out))
+    emit(out)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries the ONE JSON line and nothing else: native libraries (NCCL prints its version banner there) get
+    stderr for the rest of the run, the JSON line is written to the original descriptor by emit()."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(record):
+    line = (json.dumps(record) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
@@ -298,7 +321,7 @@ def main():
                         "allreduce, reconstruction, D2H) through the public API")
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:   # the CPU baseline is reported at N = 1 only
         cpu = cpu_sample(model, w, 0)[0]
 
     if rank == 0:
@@ -314,7 +337,7 @@ def main():
                                timing="CUDA events on the engine stream around the whole moments phase, max over ranks"),
                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
                    moment_checksum=float(np.abs(moments).sum()))
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
