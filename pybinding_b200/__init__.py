@@ -7,7 +7,8 @@ from .chebyshev import (KPM, kpm, kpm_cuda, SpatialLDOS, Deferred, jackson_kerne
                         dirichlet_kernel)
 from .results import Series
 from . import synthetic
+from . import parallel
 from .synthetic import graphene_rectangle, cubic_anderson, Rectangle
 
 __all__ = ["KPM", "kpm", "kpm_cuda", "SpatialLDOS", "Deferred", "jackson_kernel", "lorentz_kernel",
-           "dirichlet_kernel", "Series", "synthetic", "graphene_rectangle", "cubic_anderson", "Rectangle"]
+           "dirichlet_kernel", "Series", "synthetic", "parallel", "graphene_rectangle", "cubic_anderson", "Rectangle"]
