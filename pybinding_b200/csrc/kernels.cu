@@ -423,7 +423,7 @@ __global__ void cone_extract_kernel(const T* __restrict__ val, const int32_t* __
 /// each): blockIdx.y selects the sub-system, blockIdx.x strides over its rows of this step.  Step k reads r_{k-1} from
 /// buf[(k-1)&1], overwrites r_{k-2} in buf[k&1] with r_k, and the last block of each sub-system writes its two moments
 /// (same arithmetic and reductions as `cheb_step` with R = 1).  k == 1 is the initial step r_1 = H~ r_0 / 2.
-template<class T>
+template<class T, int K>   // K > 0: ELL width known at compile time (all index / value / gather loads of a row in flight together)
 __global__ void __launch_bounds__(256) cone_group_step_kernel(const ConeSlot* __restrict__ slots, int k, int kell, int M,
                                                               double* partials, unsigned* counters) {
     constexpr int C = ST<T>::C;
@@ -439,10 +439,20 @@ __global__ void __launch_bounds__(256) cone_group_step_kernel(const ConeSlot* __
     for (int q = 0; q < C; ++q) acc[q] = 0.0;
     for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < nrows; row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         T r = init ? zero_(T{}) : neg_(y[row]);
-        for (int s = 0; s < kell; ++s) {
-            int32_t const c = __ldg(col + s * sl.pitch + row);
-            T const v = ldg_scalar(val + s * sl.pitch + row);
-            r = fma_(v, ldg_scalar(x + c), r);
+        if constexpr (K > 0) {
+            int32_t c[K]; T v[K], xg[K];
+#pragma unroll
+            for (int s = 0; s < K; ++s) { c[s] = __ldg(col + s * sl.pitch + row); v[s] = ldg_scalar(val + s * sl.pitch + row); }
+#pragma unroll
+            for (int s = 0; s < K; ++s) xg[s] = ldg_scalar(x + c[s]);
+#pragma unroll
+            for (int s = 0; s < K; ++s) r = fma_(v[s], xg[s], r);
+        } else {
+            for (int s = 0; s < kell; ++s) {
+                int32_t const c = __ldg(col + s * sl.pitch + row);
+                T const v = ldg_scalar(val + s * sl.pitch + row);
+                r = fma_(v, ldg_scalar(x + c), r);
+            }
         }
         if (init) r = scale_(r, 0.5);
         sums_(acc, ldg_scalar(x + row), r);
@@ -566,7 +576,12 @@ cudaError_t launch_cone_group_step(int dtype, const ConeSlot* slots_dev, int nsl
     if (need < 1) need = 1;
     int const gx = static_cast<int>(need < blocks_per_slot_cap ? need : blocks_per_slot_cap);
     dim3 const grid(gx, nslots);
-    PBK_DISPATCH(dtype, (cone_group_step_kernel<T><<<grid, 256, 0, s>>>(slots_dev, k, kell, M, partials, counters)));
+    switch (kell) {
+        case 3: PBK_DISPATCH(dtype, (cone_group_step_kernel<T, 3><<<grid, 256, 0, s>>>(slots_dev, k, kell, M, partials, counters))); break;
+        case 4: PBK_DISPATCH(dtype, (cone_group_step_kernel<T, 4><<<grid, 256, 0, s>>>(slots_dev, k, kell, M, partials, counters))); break;
+        case 7: PBK_DISPATCH(dtype, (cone_group_step_kernel<T, 7><<<grid, 256, 0, s>>>(slots_dev, k, kell, M, partials, counters))); break;
+        default: PBK_DISPATCH(dtype, (cone_group_step_kernel<T, 0><<<grid, 256, 0, s>>>(slots_dev, k, kell, M, partials, counters))); break;
+    }
     return cudaGetLastError();
 }
 

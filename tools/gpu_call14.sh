@@ -28,4 +28,6 @@ PY
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python /tmp/san.py > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck exit $?" >> gpurun_out/sanitizer_memcheck.log
 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python /tmp/san.py > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck exit $?" >> gpurun_out/sanitizer_racecheck.log
 timeout 600 compute-sanitizer --tool synccheck --error-exitcode 7 python /tmp/san.py > gpurun_out/sanitizer_synccheck.log 2>&1; echo "synccheck exit $?" >> gpurun_out/sanitizer_synccheck.log
+timeout 600 python -m pytest tests -m gpu -q --timeout 300 -k "parallel or graph" > gpurun_out/pytest_parallel.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_parallel.log
+tail -n 4 gpurun_out/pytest_parallel.log
 tail -n 6 gpurun_out/sanitizer_memcheck.log; tail -n 6 gpurun_out/sanitizer_racecheck.log; tail -n 6 gpurun_out/sanitizer_synccheck.log
