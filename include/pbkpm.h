@@ -185,6 +185,10 @@ int pbk_calc_conductivity(pbk_ctx* ctx, const float* left, const float* right,
 /* The relabelling used for full-system runs (see pbk_config.locality_tile): order[new_row] = original row.
  * Host-only helper (no device needed); exposed so that callers / tests can inspect the layout. */
 int pbk_locality_order(int64_t n, const int32_t* indptr, const int32_t* indices, int32_t tile, int32_t* order);
+/* Two-level variant: macro-blocks of `macro_tiles` tiles first, clusters inside each block second (macro_tiles <= 1: the
+ * one-level order above).  Tiles of a block are consecutive rows, so CTAs resident together share their halo rows in L2. */
+int pbk_locality_order2(int64_t n, const int32_t* indptr, const int32_t* indices, int32_t tile, int32_t macro_tiles,
+                        int32_t* order);
 
 /* Host-only check of the MT19937 jump-ahead used for segment-parallel starter generation: writes the 624-word
  * generator window positioned so that window[1..623] are the raw (untempered) words of draws

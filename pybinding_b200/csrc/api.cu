@@ -114,6 +114,14 @@ int pbk_locality_order(int64_t n, const int32_t* indptr, const int32_t* indices,
     return PBK_OK;
 }
 
+int pbk_locality_order2(int64_t n, const int32_t* indptr, const int32_t* indices, int32_t tile, int32_t macro_tiles, int32_t* order) {
+    if (n <= 0 || !indptr || !indices || !order || tile < 1 || macro_tiles < 0) return PBK_INVALID_ARGUMENT;
+    std::vector<int32_t> queue, rmap;
+    cluster_order(n, indptr, indices, tile, queue, rmap, macro_tiles);
+    std::memcpy(order, queue.data(), sizeof(int32_t) * static_cast<size_t>(n));
+    return PBK_OK;
+}
+
 int pbk_shard(int32_t total, int32_t world_size, int32_t rank, int32_t* first, int32_t* count) {
     if (total < 0 || world_size < 1 || rank < 0 || rank >= world_size || !first || !count) return PBK_INVALID_ARGUMENT;
     int f = 0, c = 0;

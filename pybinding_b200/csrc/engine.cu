@@ -15,6 +15,7 @@
 #include "engine.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -158,6 +159,7 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     bulk_stages = static_cast<int>(env_int("PBK_BULK", 4));
     bulk_xstage = env_int("PBK_XS", 1) != 0;
     identity_order = env_int("PBK_IDENTITY_ORDER", 0) != 0;
+    macro_tiles = env_int("PBK_MACRO", 256);   // 65 k-site macro-blocks: +4 % on configs[1] (profiles/r01_sweep_macro_full_v5.log)
     cone_mode = static_cast<int>(env_int("PBK_CONE", 1));
     graph_mode = static_cast<int>(env_int("PBK_GRAPH", 1));
     graph_max_bytes = 1e6 * static_cast<double>(env_int("PBK_GRAPH_MAX_MB", 64));
@@ -202,7 +204,7 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
     std::thread ordering;
     if (locality_tile > 0 && !identity_order) {
         cluster_tile = locality_tile;
-        ordering = std::thread([this, n_, indptr, indices] { cluster_order(n_, indptr, indices, cluster_tile, cluster_queue, cluster_rmap); });
+        ordering = std::thread([this, n_, indptr, indices] { cluster_order(n_, indptr, indices, cluster_tile, cluster_queue, cluster_rmap, macro_tiles); });
     }
     h_indptr.resize_uninit(static_cast<size_t>(n) + 1);
     h_indices.resize_uninit(static_cast<size_t>(nnz));
@@ -335,8 +337,8 @@ HostEll build_ell_host(int64_t n, const int32_t* indptr, const int32_t* indices,
 /// KPM results are invariant under a relabelling of the sites; the starters are generated per *original* site
 /// index and scattered through the map, exactly like the reference does with its own reorder map
 /// (cppcore/src/kpm/Starter.cpp:68,80).  Fills queue (new -> old) and rmap (old -> new).
-void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int64_t tile,
-                          std::vector<int32_t>& queue, std::vector<int32_t>& rmap) {
+void cluster_order_flat(int64_t n, const int32_t* indptr, const int32_t* indices, int64_t tile,
+                        std::vector<int32_t>& queue, std::vector<int32_t>& rmap) {
     queue.clear();
     queue.reserve(n);
     rmap.assign(n, -1);
@@ -385,6 +387,59 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
             for (int p = indptr[row]; p < indptr[row + 1]; ++p) if (rmap[indices[p]] < 0) seeds.push_back(indices[p]);
         }
     }
+}
+
+/// Two-level locality ordering: macro-blocks of `macro_tiles` tiles (breadth-first balls grown like the clusters, which keeps
+/// every block compact), then the clusters inside each block, blocks in parallel.  The tiles of a macro-block are consecutive
+/// rows, so the CTAs that are resident together work on neighbouring clusters and a halo row fetched by one of them is an
+/// L2 hit for the others; only the halo of the macro-block boundary is read from DRAM twice.  macro_tiles <= 1: one level.
+void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int64_t tile,
+                   std::vector<int32_t>& queue, std::vector<int32_t>& rmap, int64_t macro_tiles) {
+    int64_t const macro = macro_tiles * tile;
+    if (macro_tiles <= 1 || macro >= n) { cluster_order_flat(n, indptr, indices, tile, queue, rmap); return; }
+    std::vector<int32_t> q1, r1;
+    cluster_order_flat(n, indptr, indices, macro, q1, r1);
+    queue.assign(n, 0);
+    rmap.assign(n, -1);
+    int64_t const nblocks = (n + macro - 1) / macro;
+    auto order_block = [&](int64_t m) {
+        int64_t const lo = m * macro, hi = std::min<int64_t>(n, lo + macro);
+        auto inside = [&](int32_t site) { int64_t const p = r1[site]; return p >= lo && p < hi; };
+        int64_t filled = lo;             // next position of the final order
+        std::vector<int32_t> seeds;
+        size_t seed_head = 0;
+        int64_t scan = lo;               // next_unvisited over the block's sites in level-1 order
+        while (filled < hi) {
+            int32_t seed = -1;
+            while (seed_head < seeds.size()) { int32_t const c = seeds[seed_head++]; if (rmap[c] < 0) { seed = c; break; } }
+            if (seed < 0) { while (rmap[q1[scan]] >= 0) ++scan; seed = q1[scan]; }
+            int64_t const begin = filled;
+            int64_t const limit = std::min<int64_t>(hi, (begin - lo) / tile * tile + lo + tile);   // tiles stay aligned inside the block
+            rmap[seed] = static_cast<int32_t>(filled); queue[filled++] = seed;
+            int64_t head = begin;
+            bool full = filled >= limit;
+            while (head < filled && !full) {
+                int32_t const row = queue[head];
+                for (int p = indptr[row]; p < indptr[row + 1]; ++p) {
+                    int32_t const c = indices[p];
+                    if (!inside(c) || rmap[c] >= 0) continue;
+                    if (filled >= limit) { full = true; break; }
+                    rmap[c] = static_cast<int32_t>(filled); queue[filled++] = c;
+                }
+                if (!full) ++head;
+            }
+            for (int64_t q = head; q < filled; ++q) {
+                int32_t const row = queue[q];
+                for (int p = indptr[row]; p < indptr[row + 1]; ++p) { int32_t const c = indices[p]; if (inside(c) && rmap[c] < 0) seeds.push_back(c); }
+            }
+        }
+    };
+    int nt = static_cast<int>(std::thread::hardware_concurrency());
+    nt = std::max(1, std::min(nt, 16));
+    std::vector<std::thread> pool;
+    std::atomic<int64_t> next{0};
+    for (int t = 0; t < nt; ++t) pool.emplace_back([&] { for (int64_t m = next++; m < nblocks; m = next++) order_block(m); });
+    for (auto& th : pool) th.join();
 }
 
 /// BFS relabelling from src[0]; slice k = the k-th shell (OptimizedHamiltonian.cpp:88-143)
@@ -501,7 +556,7 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
             dh.reorder_map = std::move(cluster_rmap);
             cluster_queue.clear(); cluster_rmap.clear(); cluster_tile = 0;
         } else {
-            cluster_order(n, h_indptr.data(), h_indices.data(), locality_tile, queue, dh.reorder_map);
+            cluster_order(n, h_indptr.data(), h_indices.data(), locality_tile, queue, dh.reorder_map, macro_tiles);
         }
         for (int32_t i : target.src) dh.idx.src.push_back(dh.reorder_map[i]);
         for (int32_t i : target.dest) dh.idx.dest.push_back(dh.reorder_map[i]);
