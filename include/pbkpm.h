@@ -67,8 +67,9 @@ typedef struct pbk_config {
     float lanczos_precision; /* percent, default 0.002 */
     int32_t max_batch;       /* max. KPM vectors advanced together in one pass over H (0 = automatic) */
     int32_t locality_tile;   /* full-system runs (DOS, conductivity, moments): sites are relabelled into breadth-first
-                                clusters of this many rows so that gathers stay on-chip; 0 = automatic, < 0 = keep
-                                the caller's site order.  Results do not depend on it beyond summation rounding. */
+                                clusters of this many rows (grouped into macro-blocks of 256 clusters) so that gathers
+                                stay on-chip; 0 = automatic, < 0 = keep the caller's site order.  Results do not
+                                depend on it beyond summation rounding. */
 } pbk_config;
 
 /* kpm::Stats (cppcore/include/kpm/Stats.hpp:19-45, cppmodule/src/kpm.cpp:50-66) + GPU counters. */

@@ -2,16 +2,18 @@
 // OptimizedHamiltonian, Starter and DefaultCompute: cppcore/src/kpm/*.cpp of the reference).
 //
 // Design (B200-first, not a port):
-//  * the scaled Hamiltonian lives on the device in slot-major ELL; stochastic quantities (DOS,
-//    conductivity, moments) use the *original* site order -- results are permutation invariant and the
-//    lattice order already gives banded, L2-friendly gathers -- while unit-vector quantities (LDOS,
-//    Green's) use a breadth-first relabelling from the source so that the light cone of the recursion is
-//    a row prefix (`SliceMap`) and each step only touches `optimal_size(n)` rows;
-//  * all R vectors of a batch are advanced by ONE fused kernel launch per Chebyshev step; the moments are
-//    produced on the device by the kernel's last block, so a whole recursion is an uninterrupted stream
-//    of launches with a single device->host copy of the finished moments at the end;
-//  * random starters are the reference's own MT19937 stream, generated on the device;
-//  * multi-GPU: vectors are sharded over ranks, one ncclAllReduce of the moment sums at the end.
+//  * the scaled Hamiltonian lives on the device in slot-major ELL.  Stochastic quantities (DOS, conductivity, moments)
+//    use a two-level *locality ordering* of the sites (breadth-first clusters of 256 rows inside macro-blocks of 256
+//    clusters): results are permutation invariant, a CTA owns one cluster at a time and the clusters resident together
+//    share their halo rows through L2.  Unit-vector quantities use the reference's breadth-first relabelling from the
+//    source so that the light cone of the recursion is a row prefix (`SliceMap`) and each step only touches
+//    `optimal_size(n)` rows; LDOS does this on a *sub-system* cut out of the resident matrix by a kernel (the host only
+//    walks the ball the recursion can reach), Green's relabels on the host;
+//  * all R vectors of a batch are advanced by ONE fused kernel launch per Chebyshev step; the moments are produced on
+//    the device by the kernel's last block, so a whole recursion is an uninterrupted stream of launches (replayed as a
+//    CUDA graph when the system is small enough to be launch-bound) with a single device->host copy at the end;
+//  * random starters are the reference's own MT19937 stream, generated on the device (GF(2) jump-ahead);
+//  * multi-GPU: vectors / LDOS sites are sharded over ranks, one ncclAllReduce of the moment sums at the end.
 #include "engine.hpp"
 
 #include <algorithm>
