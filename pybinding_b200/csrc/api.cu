@@ -2,6 +2,7 @@
 // entry point returns a pbk_status and stores the message in the context (pbk_last_error).
 #include "engine.hpp"
 
+#include <cstdlib>
 #include <cstring>
 
 using namespace pbk;
@@ -117,7 +118,8 @@ int pbk_locality_order(int64_t n, const int32_t* indptr, const int32_t* indices,
 int pbk_locality_order2(int64_t n, const int32_t* indptr, const int32_t* indices, int32_t tile, int32_t macro_tiles, int32_t* order) {
     if (n <= 0 || !indptr || !indices || !order || tile < 1 || macro_tiles < 0) return PBK_INVALID_ARGUMENT;
     std::vector<int32_t> queue, rmap;
-    cluster_order(n, indptr, indices, tile, queue, rmap, macro_tiles);
+    char const* coarse_env = std::getenv("PBK_COARSE");   // same knob as the engine (default 16 sites per super-node)
+    cluster_order(n, indptr, indices, tile, queue, rmap, macro_tiles, coarse_env ? std::strtol(coarse_env, nullptr, 10) : 16);
     std::memcpy(order, queue.data(), sizeof(int32_t) * static_cast<size_t>(n));
     return PBK_OK;
 }

@@ -161,6 +161,7 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     bulk_stages = static_cast<int>(env_int("PBK_BULK", 4));
     bulk_xstage = env_int("PBK_XS", 1) != 0;
     identity_order = env_int("PBK_IDENTITY_ORDER", 0) != 0;
+    coarse_sites = env_int("PBK_COARSE", 16);
     macro_tiles = env_int("PBK_MACRO", 256);   // 65 k-site macro-blocks: +4 % on configs[1] (profiles/r01_sweep_macro_full_v5.log)
     cone_mode = static_cast<int>(env_int("PBK_CONE", 1));
     graph_mode = static_cast<int>(env_int("PBK_GRAPH", 1));
@@ -206,7 +207,7 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
     std::thread ordering;
     if (locality_tile > 0 && !identity_order) {
         cluster_tile = locality_tile;
-        ordering = std::thread([this, n_, indptr, indices] { cluster_order(n_, indptr, indices, cluster_tile, cluster_queue, cluster_rmap, macro_tiles); });
+        ordering = std::thread([this, n_, indptr, indices] { cluster_order(n_, indptr, indices, cluster_tile, cluster_queue, cluster_rmap, macro_tiles, coarse_sites); });
     }
     h_indptr.resize_uninit(static_cast<size_t>(n) + 1);
     h_indices.resize_uninit(static_cast<size_t>(nnz));
@@ -391,30 +392,86 @@ void cluster_order_flat(int64_t n, const int32_t* indptr, const int32_t* indices
     }
 }
 
-/// Two-level locality ordering: macro-blocks of `macro_tiles` tiles (breadth-first balls grown like the clusters, which keeps
-/// every block compact), then the clusters inside each block, blocks in parallel.  The tiles of a macro-block are consecutive
-/// rows, so the CTAs that are resident together work on neighbouring clusters and a halo row fetched by one of them is an
-/// L2 hit for the others; only the halo of the macro-block boundary is read from DRAM twice.  macro_tiles <= 1: one level.
+/// Two-level locality ordering: macro-blocks of `macro_tiles` tiles, then the clusters inside each block, blocks in
+/// parallel.  The tiles of a macro-block are consecutive rows, so the CTAs that are resident together work on
+/// neighbouring clusters and a halo row fetched by one of them is an L2 hit for the others; only the halo of the
+/// macro-block boundary is read from DRAM twice.  macro_tiles <= 1: one level.
+///
+/// The macro-blocks are breadth-first balls too, but of a *coarsened* graph on large systems: `coarse` consecutive sites
+/// of the caller's order form one super-node (lattice generators number neighbouring cells consecutively; for an
+/// arbitrary order the blocks are merely less compact, the clusters inside them are still grown on the real graph).
+/// The coarse graph is built by a parallel pass over the CSR and its ball growing is `coarse` times cheaper than the
+/// serial pass over all sites, which was the largest host cost of `set_hamiltonian`.  Every step is deterministic.
 void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int64_t tile,
-                   std::vector<int32_t>& queue, std::vector<int32_t>& rmap, int64_t macro_tiles) {
+                   std::vector<int32_t>& queue, std::vector<int32_t>& rmap, int64_t macro_tiles, int64_t coarse) {
     int64_t const macro = macro_tiles * tile;
     if (macro_tiles <= 1 || macro >= n) { cluster_order_flat(n, indptr, indices, tile, queue, rmap); return; }
-    std::vector<int32_t> q1, r1;
-    cluster_order_flat(n, indptr, indices, macro, q1, r1);
+
+    // ---- level 1: sites in block order (lvl1), block borders (bstart), block of every site (blk) ----
+    std::vector<int32_t> lvl1, blk(static_cast<size_t>(n));
+    std::vector<int64_t> bstart;
+    bool const use_coarse = coarse > 1 && macro % coarse == 0 && macro / coarse >= 1024 && n >= 8 * macro;   // blocks of >= 1024 super-nodes stay compact
+    if (!use_coarse) {
+        std::vector<int32_t> r1;
+        cluster_order_flat(n, indptr, indices, macro, lvl1, r1);
+        for (int64_t b = 0; b * macro < n; ++b) bstart.push_back(b * macro);
+        bstart.push_back(n);
+        parallel_rows(n, [&](int64_t b, int64_t e) { for (int64_t i = b; i < e; ++i) blk[i] = static_cast<int32_t>(r1[i] / macro); });
+    } else {
+        int64_t const ns = (n + coarse - 1) / coarse;       // super-node s = sites [s * coarse, (s + 1) * coarse)
+        int64_t const mc = macro / coarse;                  // super-nodes per block
+        std::vector<int32_t> cptr(static_cast<size_t>(ns) + 1, 0), cidx;
+        auto neighbours = [&](int64_t sn, std::vector<int32_t>& buf) {
+            buf.clear();
+            int64_t const lo = sn * coarse, hi = std::min<int64_t>(n, lo + coarse);
+            for (int p = indptr[lo]; p < indptr[hi]; ++p) { int32_t const c = static_cast<int32_t>(indices[p] / coarse); if (c != sn) buf.push_back(c); }
+            std::sort(buf.begin(), buf.end());
+            buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
+        };
+        parallel_rows(ns, [&](int64_t b, int64_t e) { std::vector<int32_t> buf; for (int64_t sn = b; sn < e; ++sn) { neighbours(sn, buf); cptr[sn + 1] = static_cast<int32_t>(buf.size()); } });
+        for (int64_t sn = 0; sn < ns; ++sn) cptr[sn + 1] += cptr[sn];
+        cidx.resize(static_cast<size_t>(cptr[ns]));
+        parallel_rows(ns, [&](int64_t b, int64_t e) { std::vector<int32_t> buf; for (int64_t sn = b; sn < e; ++sn) { neighbours(sn, buf); std::copy(buf.begin(), buf.end(), cidx.begin() + cptr[sn]); } });
+        std::vector<int32_t> q1c, r1c;
+        cluster_order_flat(ns, cptr.data(), cidx.data(), mc, q1c, r1c);
+        // blocks of mc super-nodes in q1c order; the block holding the short last super-node goes to the end so that every
+        // other block starts on a tile boundary
+        int64_t const nb = (ns + mc - 1) / mc;
+        std::vector<int64_t> order(nb);
+        for (int64_t b = 0; b < nb; ++b) order[b] = b;
+        if (n % coarse != 0) {
+            int64_t const odd = r1c[ns - 1] / mc;
+            order.erase(order.begin() + odd);
+            order.push_back(odd);
+        }
+        lvl1.resize(static_cast<size_t>(n));
+        bstart.assign(1, 0);
+        for (int64_t ob = 0; ob < nb; ++ob) {
+            int64_t const b = order[ob];
+            int64_t pos = bstart.back();
+            for (int64_t j = b * mc; j < std::min<int64_t>(ns, (b + 1) * mc); ++j) {
+                int64_t const sn = q1c[j];
+                for (int64_t i = sn * coarse; i < std::min<int64_t>(n, (sn + 1) * coarse); ++i) { lvl1[pos++] = static_cast<int32_t>(i); blk[i] = static_cast<int32_t>(ob); }
+            }
+            bstart.push_back(pos);
+        }
+    }
+
+    // ---- level 2: clusters inside every block, grown on the real graph; blocks are independent ----
     queue.assign(n, 0);
     rmap.assign(n, -1);
-    int64_t const nblocks = (n + macro - 1) / macro;
+    int64_t const nblocks = static_cast<int64_t>(bstart.size()) - 1;
     auto order_block = [&](int64_t m) {
-        int64_t const lo = m * macro, hi = std::min<int64_t>(n, lo + macro);
-        auto inside = [&](int32_t site) { int64_t const p = r1[site]; return p >= lo && p < hi; };
+        int64_t const lo = bstart[m], hi = bstart[m + 1];
+        int32_t const me = static_cast<int32_t>(m);
         int64_t filled = lo;             // next position of the final order
         std::vector<int32_t> seeds;
         size_t seed_head = 0;
-        int64_t scan = lo;               // next_unvisited over the block's sites in level-1 order
+        int64_t scan = lo;               // next unvisited site of the block in level-1 order
         while (filled < hi) {
             int32_t seed = -1;
             while (seed_head < seeds.size()) { int32_t const c = seeds[seed_head++]; if (rmap[c] < 0) { seed = c; break; } }
-            if (seed < 0) { while (rmap[q1[scan]] >= 0) ++scan; seed = q1[scan]; }
+            if (seed < 0) { while (rmap[lvl1[scan]] >= 0) ++scan; seed = lvl1[scan]; }
             int64_t const begin = filled;
             int64_t const limit = std::min<int64_t>(hi, (begin - lo) / tile * tile + lo + tile);   // tiles stay aligned inside the block
             rmap[seed] = static_cast<int32_t>(filled); queue[filled++] = seed;
@@ -424,7 +481,7 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
                 int32_t const row = queue[head];
                 for (int p = indptr[row]; p < indptr[row + 1]; ++p) {
                     int32_t const c = indices[p];
-                    if (!inside(c) || rmap[c] >= 0) continue;
+                    if (blk[c] != me || rmap[c] >= 0) continue;
                     if (filled >= limit) { full = true; break; }
                     rmap[c] = static_cast<int32_t>(filled); queue[filled++] = c;
                 }
@@ -432,7 +489,7 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
             }
             for (int64_t q = head; q < filled; ++q) {
                 int32_t const row = queue[q];
-                for (int p = indptr[row]; p < indptr[row + 1]; ++p) { int32_t const c = indices[p]; if (inside(c) && rmap[c] < 0) seeds.push_back(c); }
+                for (int p = indptr[row]; p < indptr[row + 1]; ++p) { int32_t const c = indices[p]; if (blk[c] == me && rmap[c] < 0) seeds.push_back(c); }
             }
         }
     };
@@ -558,7 +615,7 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
             dh.reorder_map = std::move(cluster_rmap);
             cluster_queue.clear(); cluster_rmap.clear(); cluster_tile = 0;
         } else {
-            cluster_order(n, h_indptr.data(), h_indices.data(), locality_tile, queue, dh.reorder_map, macro_tiles);
+            cluster_order(n, h_indptr.data(), h_indices.data(), locality_tile, queue, dh.reorder_map, macro_tiles, coarse_sites);
         }
         for (int32_t i : target.src) dh.idx.src.push_back(dh.reorder_map[i]);
         for (int32_t i : target.dest) dh.idx.dest.push_back(dh.reorder_map[i]);

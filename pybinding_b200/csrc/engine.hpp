@@ -256,6 +256,7 @@ private:
     DevBuf vec_c, vec_d;         // second vector pair of the two-step kernel
     DevBuf cone_val, cone_col, cone_queue, cone_gmap, cone_table;   // light-cone sub-system of the site being processed
     int64_t cone_gmap_rows = 0;  // cone_gmap holds -1 for this many rows
+    int64_t coarse_sites = 16;   // PBK_COARSE: consecutive sites per super-node of the macro-block pass (1: no coarsening)
     int64_t macro_tiles = 256;   // PBK_MACRO: tiles per macro-block of the two-level locality ordering (0: one level)
     bool identity_order = false; // PBK_IDENTITY_ORDER=1: tiles of consecutive rows in the caller's order instead of locality clusters
     int cone_mode = 1;           // PBK_CONE=0: the previous host-side full BFS relabelling for LDOS
@@ -331,7 +332,7 @@ void shard_range(int total, int world, int rank, int* first, int* count);
 
 /// locality relabelling of the full-system layout (engine.cu)
 void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int64_t tile,
-                   std::vector<int32_t>& queue, std::vector<int32_t>& rmap, int64_t macro_tiles = 0);
+                   std::vector<int32_t>& queue, std::vector<int32_t>& rmap, int64_t macro_tiles = 0, int64_t coarse = 16);
 
 // kernels (src/kpm/Kernel.cpp:6-49)
 int round_num_moments(int n);

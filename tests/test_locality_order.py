@@ -47,9 +47,10 @@ def test_graphene_order_is_a_compact_permutation(macro):
         assert np.array_equal(order, order_of(h, 256))              # deterministic
 
 
-def test_two_level_order_is_deterministic_and_blocks_are_closed_under_the_first_level():
+def test_two_level_order_is_deterministic_and_blocks_are_closed_under_the_first_level(monkeypatch):
     h = pb.graphene_rectangle(60.0, dtype=np.float32).hamiltonian.tocsr()
     n, tile, macro = h.shape[0], 128, 8
+    monkeypatch.setenv("PBK_COARSE", "1")                           # macro-blocks grown on the real graph
     a, b = order_of(h, tile, macro), order_of(h, tile, macro)
     assert np.array_equal(a, b)                                     # thread schedule does not leak into the result
     level1 = order_of(h, tile * macro)                              # the macro-blocks are the clusters of this order
@@ -57,6 +58,25 @@ def test_two_level_order_is_deterministic_and_blocks_are_closed_under_the_first_
     for m in range(0, n, block):
         assert set(a[m:m + block]) == set(level1[m:m + block])
     assert halo_fraction(h, a, tile) <= halo_fraction(h, order_of(h, tile), tile) + 0.05
+
+
+def test_coarsened_macro_blocks(monkeypatch):
+    """Large systems grow the macro-blocks on a coarsened graph (16 consecutive sites per super-node): still a
+    deterministic permutation with compact tiles, and every block but the ones moved to the end is made of whole
+    super-nodes and starts on a tile boundary"""
+    h = pb.graphene_rectangle(100.0, dtype=np.float32).hamiltonian.tocsr()    # 382 k sites >= 8 macro-blocks of 16 k
+    n, tile, macro = h.shape[0], 256, 64
+    monkeypatch.setenv("PBK_COARSE", "16")
+    a = order_of(h, tile, macro)
+    assert np.array_equal(np.sort(a), np.arange(n))
+    assert np.array_equal(a, order_of(h, tile, macro))
+    monkeypatch.setenv("PBK_COARSE", "1")
+    fine = order_of(h, tile, macro)
+    assert not np.array_equal(a, fine)                              # the coarse pass was really used
+    assert halo_fraction(h, a, tile) < halo_fraction(h, fine, tile) + 0.03
+    block = tile * macro
+    first = a[:block]                                               # a regular block: whole super-nodes of 16 sites
+    assert np.array_equal(np.unique(first // 16).repeat(16), np.sort(first) // 16)
 
 
 def test_cubic_order_is_a_permutation():
