@@ -39,7 +39,7 @@ def main():
         env = dict(kv.split("=") for kv in cfg.split(",") if kv)
         max_batch = int(env.pop("MB", 0))   # pseudo-key: vectors per pass
         for k in ("PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL", "PBK_BULK", "PBK_XS",
-                  "PBK_PAIR", "PBK_PAIR_STAGES", "PBK_PAIR_MINB", "PBK_PAIR_R", "PBK_IDENTITY_ORDER", "PBK_MACRO"):
+                  "PBK_PAIR", "PBK_PAIR_STAGES", "PBK_PAIR_MINB", "PBK_PAIR_R", "PBK_IDENTITY_ORDER", "PBK_MACRO", "PBK_COARSE"):
             os.environ.pop(k, None)
         os.environ.update(env)
         t0 = time.time()
