@@ -62,11 +62,11 @@ static double now_seconds() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-template<class F> static void parallel_rows(int64_t n, F fn) {
+template<class F> static void parallel_rows(int64_t n, F fn, int64_t min_items = int64_t{1} << 16) {
     int nt = static_cast<int>(std::thread::hardware_concurrency());
     if (nt < 1) nt = 1;
     if (nt > 16) nt = 16;
-    if (n < (1 << 16)) nt = 1;
+    if (n < min_items) nt = 1;
     if (nt == 1) { fn(int64_t{0}, n); return; }
     std::vector<std::thread> threads;
     int64_t const chunk = (n + nt - 1) / nt;
@@ -201,6 +201,7 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
     dtype = dt;
     n = n_;
     int64_t const nnz = indptr[n];
+    double const t_set0 = now_seconds();
     // the locality ordering of the full-system layout only needs the sparsity pattern: it runs on the caller's arrays in
     // a second thread while this one copies them (parallel first touch)
     cluster_queue.clear(); cluster_rmap.clear(); cluster_tile = 0;
@@ -218,7 +219,9 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
         size_t const sz = dtype_size(dt);
         std::memcpy(h_data.data() + b * sz, static_cast<const char*>(data) + b * sz, sz * static_cast<size_t>(e - b));
     });
+    double const t_copy = now_seconds();
     if (ordering.joinable()) ordering.join();
+    if (std::getenv("PBK_TIMING")) std::fprintf(stderr, "[pbkpm] set_hamiltonian: copy %.3f s, + wait for the ordering %.3f s\n", t_copy - t_set0, now_seconds() - t_copy);
     has_h = true;
     clear_graphs();
     natural = DeviceHamiltonian();
@@ -406,6 +409,14 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
                    std::vector<int32_t>& queue, std::vector<int32_t>& rmap, int64_t macro_tiles, int64_t coarse) {
     int64_t const macro = macro_tiles * tile;
     if (macro_tiles <= 1 || macro >= n) { cluster_order_flat(n, indptr, indices, tile, queue, rmap); return; }
+    bool const timing = std::getenv("PBK_TIMING") != nullptr;
+    double t_mark = now_seconds();
+    auto mark = [&](char const* what) {
+        if (!timing) return;
+        double const t = now_seconds();
+        std::fprintf(stderr, "[pbkpm] cluster_order: %-24s %.3f s\n", what, t - t_mark);
+        t_mark = t;
+    };
 
     // ---- level 1: sites in block order (lvl1), block borders (bstart), block of every site (blk) ----
     std::vector<int32_t> lvl1, blk(static_cast<size_t>(n));
@@ -420,20 +431,38 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
     } else {
         int64_t const ns = (n + coarse - 1) / coarse;       // super-node s = sites [s * coarse, (s + 1) * coarse)
         int64_t const mc = macro / coarse;                  // super-nodes per block
-        std::vector<int32_t> cptr(static_cast<size_t>(ns) + 1, 0), cidx;
-        auto neighbours = [&](int64_t sn, std::vector<int32_t>& buf) {
-            buf.clear();
-            int64_t const lo = sn * coarse, hi = std::min<int64_t>(n, lo + coarse);
-            for (int p = indptr[lo]; p < indptr[hi]; ++p) { int32_t const c = static_cast<int32_t>(indices[p] / coarse); if (c != sn) buf.push_back(c); }
-            std::sort(buf.begin(), buf.end());
-            buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
-        };
-        parallel_rows(ns, [&](int64_t b, int64_t e) { std::vector<int32_t> buf; for (int64_t sn = b; sn < e; ++sn) { neighbours(sn, buf); cptr[sn + 1] = static_cast<int32_t>(buf.size()); } });
-        for (int64_t sn = 0; sn < ns; ++sn) cptr[sn + 1] += cptr[sn];
-        cidx.resize(static_cast<size_t>(cptr[ns]));
-        parallel_rows(ns, [&](int64_t b, int64_t e) { std::vector<int32_t> buf; for (int64_t sn = b; sn < e; ++sn) { neighbours(sn, buf); std::copy(buf.begin(), buf.end(), cidx.begin() + cptr[sn]); } });
+        // coarse adjacency with a fixed stride: at most CAP distinct neighbouring super-nodes, in first-occurrence order
+        // (deterministic), unused slots point to the node itself (ignored by the ball growing)
+        constexpr int CAP = 16;
+        std::vector<int32_t> cptr(static_cast<size_t>(ns) + 1), cidx(static_cast<size_t>(ns) * CAP);
+        std::atomic<bool> overflow{false};
+        parallel_rows(ns, [&](int64_t b, int64_t e) {
+            for (int64_t sn = b; sn < e; ++sn) {
+                int32_t* const out = cidx.data() + sn * CAP;
+                int cnt = 0;
+                int64_t const lo = sn * coarse, hi = std::min<int64_t>(n, lo + coarse);
+                for (int p = indptr[lo]; p < indptr[hi]; ++p) {
+                    int32_t const c = static_cast<int32_t>(indices[p] / coarse);
+                    if (c == sn) continue;
+                    bool seen = false;
+                    for (int q = 0; q < cnt; ++q) seen |= (out[q] == c);
+                    if (seen) continue;
+                    if (cnt == CAP) { overflow = true; break; }
+                    out[cnt++] = c;
+                }
+                for (int q = cnt; q < CAP; ++q) out[q] = static_cast<int32_t>(sn);
+                cptr[sn] = static_cast<int32_t>(sn * CAP);
+            }
+        });
+        cptr[ns] = static_cast<int32_t>(ns * CAP);
+        if (overflow || ns * CAP >= (int64_t{1} << 31)) {   // denser than a lattice: grow the macro-blocks on the real graph instead
+            cluster_order(n, indptr, indices, tile, queue, rmap, macro_tiles, 1);
+            return;
+        }
+        mark("coarse graph");
         std::vector<int32_t> q1c, r1c;
         cluster_order_flat(ns, cptr.data(), cidx.data(), mc, q1c, r1c);
+        mark("macro-blocks (coarse)");
         // blocks of mc super-nodes in q1c order; the block holding the short last super-node goes to the end so that every
         // other block starts on a tile boundary
         int64_t const nb = (ns + mc - 1) / mc;
@@ -446,20 +475,32 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
         }
         lvl1.resize(static_cast<size_t>(n));
         bstart.assign(1, 0);
-        for (int64_t ob = 0; ob < nb; ++ob) {
+        for (int64_t ob = 0; ob < nb; ++ob) {   // block sizes first, so that the expansion below can run block-parallel
             int64_t const b = order[ob];
-            int64_t pos = bstart.back();
+            int64_t size = 0;
             for (int64_t j = b * mc; j < std::min<int64_t>(ns, (b + 1) * mc); ++j) {
                 int64_t const sn = q1c[j];
-                for (int64_t i = sn * coarse; i < std::min<int64_t>(n, (sn + 1) * coarse); ++i) { lvl1[pos++] = static_cast<int32_t>(i); blk[i] = static_cast<int32_t>(ob); }
+                size += std::min<int64_t>(n, (sn + 1) * coarse) - sn * coarse;
             }
-            bstart.push_back(pos);
+            bstart.push_back(bstart.back() + size);
         }
+        parallel_rows(nb, [&](int64_t b0, int64_t b1) {
+            for (int64_t ob = b0; ob < b1; ++ob) {
+                int64_t const b = order[ob];
+                int64_t pos = bstart[ob];
+                for (int64_t j = b * mc; j < std::min<int64_t>(ns, (b + 1) * mc); ++j) {
+                    int64_t const sn = q1c[j];
+                    for (int64_t i = sn * coarse; i < std::min<int64_t>(n, (sn + 1) * coarse); ++i) { lvl1[pos++] = static_cast<int32_t>(i); blk[i] = static_cast<int32_t>(ob); }
+                }
+            }
+        }, 2);
     }
 
+    mark("level-1 expansion");
     // ---- level 2: clusters inside every block, grown on the real graph; blocks are independent ----
     queue.assign(n, 0);
     rmap.assign(n, -1);
+    mark("output arrays");
     int64_t const nblocks = static_cast<int64_t>(bstart.size()) - 1;
     auto order_block = [&](int64_t m) {
         int64_t const lo = bstart[m], hi = bstart[m + 1];
@@ -499,6 +540,7 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
     std::atomic<int64_t> next{0};
     for (int t = 0; t < nt; ++t) pool.emplace_back([&] { for (int64_t m = next++; m < nblocks; m = next++) order_block(m); });
     for (auto& th : pool) th.join();
+    mark("clusters inside blocks");
 }
 
 /// BFS relabelling from src[0]; slice k = the k-th shell (OptimizedHamiltonian.cpp:88-143)
@@ -604,6 +646,14 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
     dh = DeviceHamiltonian();
     bool const reorder = order != ORDER_NATURAL;
 
+    bool const timing = std::getenv("PBK_TIMING") != nullptr;
+    double t_mark = now_seconds();
+    auto mark = [&](char const* what) {
+        if (!timing) return;
+        double const t = now_seconds();
+        std::fprintf(stderr, "[pbkpm] build_device_hamiltonian: %-28s %.3f s\n", what, t - t_mark);
+        t_mark = t;
+    };
     std::vector<int32_t> queue;
     if (order == ORDER_CLUSTER) {
         if (identity_order) {   // PBK_IDENTITY_ORDER=1: the caller's site order, cut into tiles of consecutive rows (staged kernel applies)
@@ -646,6 +696,7 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
     HostEll ell;
     const int32_t* q = reorder ? queue.data() : nullptr;
     const int32_t* rm = reorder ? dh.reorder_map.data() : nullptr;
+    mark("row order");
     if (order == ORDER_CLUSTER) dh.order_queue = queue;  // operators of the same calculation are laid out alike
     // the full-system layout (the big, long-lived one) is staged in the context's page-locked buffers
     PinnedBuf* const sv = (&dh == &natural) ? &stage_val : nullptr;
@@ -656,8 +707,10 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
         case F64: ell = build_ell_host<double>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const double*>(h_data.data()), scaled, s, q, rm, sv, sc); break;
         default: ell = build_ell_host<cd>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cd*>(h_data.data()), scaled, s, q, rm, sv, sc); break;
     }
+    mark("scaled ELL on the host");
     dh.val.alloc(ell.val_bytes);
     dh.col.alloc(ell.col_count * sizeof(int32_t));
+    mark("device allocation");
     PBK_CUDA(cudaMemcpyAsync(dh.val.as(), ell.val, ell.val_bytes, cudaMemcpyHostToDevice, stream));
     PBK_CUDA(cudaMemcpyAsync(dh.col.as(), ell.col, ell.col_count * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
     stats.h2d_bytes += static_cast<int64_t>(ell.val_bytes + ell.col_count * sizeof(int32_t));
@@ -677,6 +730,7 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
         if (pair_mode) build_pair_metadata(dh, ell.col, ell.pitch, ell.k);
     }
     PBK_CUDA(cudaStreamSynchronize(stream));
+    mark("upload + pack");
     dh.original_idx = target;
     dh.valid = true;
     dh.seconds = now_seconds() - t0;
