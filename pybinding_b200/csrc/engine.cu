@@ -162,7 +162,7 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     bulk_xstage = env_int("PBK_XS", 1) != 0;
     identity_order = env_int("PBK_IDENTITY_ORDER", 0) != 0;
     coarse_sites = env_int("PBK_COARSE", 16);
-    macro_tiles = env_int("PBK_MACRO", 256);   // 65 k-site macro-blocks: +4 % on configs[1] (profiles/r01_sweep_macro_full_v5.log)
+    macro_tiles = env_int("PBK_MACRO", 256);   // 65 k-site macro-blocks: +4 % on configs[1] in short runs, +1.5 % in the power-capped bench (profiles/r01_ab_order_v6.log)
     cone_mode = static_cast<int>(env_int("PBK_CONE", 1));
     graph_mode = static_cast<int>(env_int("PBK_GRAPH", 1));
     graph_max_bytes = 1e6 * static_cast<double>(env_int("PBK_GRAPH_MAX_MB", 64));
