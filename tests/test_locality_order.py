@@ -85,3 +85,19 @@ def test_cubic_order_is_a_permutation():
         order = order_of(h, 256, macro)
         assert np.array_equal(np.sort(order), np.arange(h.shape[0]))
         assert halo_fraction(h, order, 256) < 2.0                   # natural order: 4.0 + 2 neighbours in the line
+
+
+def test_dense_random_graph_falls_back_to_the_fine_macro_pass():
+    """More than 16 distinct neighbouring super-nodes per super-node (no lattice structure in the caller's order): the
+    coarse adjacency overflows and the macro-blocks are grown on the real graph; still a permutation"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+    n = 140_000
+    rows = np.repeat(np.arange(n), 4)
+    cols = rng.integers(0, n, size=rows.size)
+    a = sp.coo_matrix((np.ones(rows.size, np.float32), (rows, cols)), shape=(n, n)).tocsr()
+    h = (a + a.T).tocsr()
+    h.sort_indices()
+    order = order_of(h, 256, 64)            # 8 macro-blocks of 16 k sites: the coarse pass is attempted first
+    assert np.array_equal(np.sort(order), np.arange(n))
+    assert np.array_equal(order, order_of(h, 256, 64))
