@@ -191,6 +191,13 @@ int pbk_locality_order(int64_t n, const int32_t* indptr, const int32_t* indices,
 int pbk_locality_order2(int64_t n, const int32_t* indptr, const int32_t* indices, int32_t tile, int32_t macro_tiles,
                         int32_t* order);
 
+/* Host-only helper: the light cone of `src` that LDOS runs on (engine.cu: light_cone / moments_ldos_cones) -- the sites within
+ * `depth` bonds of `src` in the visiting order of the reference's relabelling (OptimizedHamiltonian.cpp:88-143: queue order,
+ * row entries in ascending column order), queue[i] = site at position i, borders[j] = sites within distance j.
+ * `queue` must hold n entries, `borders` depth + 1; *exhausted = 1 when the walk covered the whole connected component. */
+int pbk_light_cone(int64_t n, const int32_t* indptr, const int32_t* indices, int32_t src, int32_t depth,
+                   int32_t* queue, int64_t* queue_size, int32_t* borders, int32_t* num_borders, int32_t* exhausted);
+
 /* Host-only check of the MT19937 jump-ahead used for segment-parallel starter generation: writes the 624-word
  * generator window positioned so that window[1..623] are the raw (untempered) words of draws
  * [position, position + 623) of a default-seeded std::mt19937. */

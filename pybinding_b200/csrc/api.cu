@@ -124,6 +124,21 @@ int pbk_locality_order2(int64_t n, const int32_t* indptr, const int32_t* indices
     return PBK_OK;
 }
 
+int pbk_light_cone(int64_t n, const int32_t* indptr, const int32_t* indices, int32_t src, int32_t depth,
+                   int32_t* queue, int64_t* queue_size, int32_t* borders, int32_t* num_borders, int32_t* exhausted) {
+    if (n <= 0 || !indptr || !indices || src < 0 || src >= n || depth < 0 || !queue || !queue_size || !borders || !num_borders || !exhausted) {
+        return PBK_INVALID_ARGUMENT;
+    }
+    std::vector<int32_t> mark(static_cast<size_t>(n), -1);
+    Cone const c = light_cone(indptr, indices, src, depth, mark);
+    std::memcpy(queue, c.queue.data(), sizeof(int32_t) * c.queue.size());
+    std::memcpy(borders, c.borders.data(), sizeof(int32_t) * c.borders.size());
+    *queue_size = static_cast<int64_t>(c.queue.size());
+    *num_borders = static_cast<int32_t>(c.borders.size());
+    *exhausted = c.exhausted ? 1 : 0;
+    return PBK_OK;
+}
+
 int pbk_shard(int32_t total, int32_t world_size, int32_t rank, int32_t* first, int32_t* count) {
     if (total < 0 || world_size < 1 || rank < 0 || rank >= world_size || !first || !count) return PBK_INVALID_ARGUMENT;
     int f = 0, c = 0;

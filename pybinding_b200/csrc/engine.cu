@@ -1349,7 +1349,7 @@ SliceMap Cone::map() const {
     return m;
 }
 
-Cone Engine::bfs_cone(int32_t src, int depth, std::vector<int32_t>& mark) const {
+Cone light_cone(const int32_t* indptr, const int32_t* indices, int32_t src, int depth, std::vector<int32_t>& mark) {
     Cone c;
     c.queue.push_back(src);
     mark[src] = 0;
@@ -1359,8 +1359,8 @@ Cone Engine::bfs_cone(int32_t src, int depth, std::vector<int32_t>& mark) const 
         size_t const end = c.queue.size();
         for (; head < end; ++head) {
             int32_t const row = c.queue[head];
-            for (int p = h_indptr[row]; p < h_indptr[row + 1]; ++p) {
-                int32_t const col = h_indices[p];
+            for (int p = indptr[row]; p < indptr[row + 1]; ++p) {
+                int32_t const col = indices[p];
                 if (mark[col] < 0) { mark[col] = static_cast<int32_t>(c.queue.size()); c.queue.push_back(col); }
             }
         }
@@ -1369,6 +1369,10 @@ Cone Engine::bfs_cone(int32_t src, int depth, std::vector<int32_t>& mark) const 
     }
     for (int32_t site : c.queue) mark[site] = -1;
     return c;
+}
+
+Cone Engine::bfs_cone(int32_t src, int depth, std::vector<int32_t>& mark) const {
+    return light_cone(h_indptr.data(), h_indices.data(), src, depth, mark);
 }
 
 bool Engine::moments_ldos_cones(int M, Indices const& target, cd* out) {

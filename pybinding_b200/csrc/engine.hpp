@@ -330,6 +330,9 @@ private:
 /// units [first, first + count) of `total` owned by `rank` (engine.cu)
 void shard_range(int total, int world, int rank, int* first, int* count);
 
+/// truncated breadth-first walk from `src` (engine.cu); `mark` holds -1 for every site and is restored on return
+Cone light_cone(const int32_t* indptr, const int32_t* indices, int32_t src, int depth, std::vector<int32_t>& mark);
+
 /// locality relabelling of the full-system layout (engine.cu)
 void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int64_t tile,
                    std::vector<int32_t>& queue, std::vector<int32_t>& rmap, int64_t macro_tiles = 0, int64_t coarse = 16);
