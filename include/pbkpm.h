@@ -191,6 +191,14 @@ int pbk_locality_order(int64_t n, const int32_t* indptr, const int32_t* indices,
 int pbk_locality_order2(int64_t n, const int32_t* indptr, const int32_t* indices, int32_t tile, int32_t macro_tiles,
                         int32_t* order);
 
+/* Host-only test hook: the scaled slot-major ELL (element (row, s) at s * pitch + row; padding = value 0, the row's own
+ * index) exactly as it is uploaded -- OptimizedHamiltonian::create_scaled for `order` == NULL, create_reordered with the
+ * relabelling order[new_row] = old_row otherwise (cppcore/src/kpm/OptimizedHamiltonian.cpp:55-152), csr_to_ell
+ * (numeric/ellmatrix.hpp:65-82), scale factors from (min_energy, max_energy) like kpm::Scale (Bounds.hpp:19-25).
+ * Call with val == NULL to learn k and pitch first; val holds k * pitch scalars, col k * pitch int32. */
+int pbk_host_ell(int dtype, int64_t n, const int32_t* indptr, const int32_t* indices, const void* data, double min_energy,
+                 double max_energy, const int32_t* order, int32_t* k, int64_t* pitch, void* val, int32_t* col);
+
 /* Host-only helper: the light cone of `src` that LDOS runs on (engine.cu: light_cone / moments_ldos_cones) -- the sites within
  * `depth` bonds of `src` in the visiting order of the reference's relabelling (OptimizedHamiltonian.cpp:88-143: queue order,
  * row entries in ascending column order), queue[i] = site at position i, borders[j] = sites within distance j.

@@ -52,7 +52,7 @@ SYMBOLS = [
     "pbk_moments_dos", "pbk_moments_ldos", "pbk_moments_greens", "pbk_moments_kubo",
     "pbk_moments_diagonal", "pbk_random_vectors", "pbk_moments", "pbk_calc_dos", "pbk_calc_ldos",
     "pbk_calc_greens", "pbk_calc_conductivity", "pbk_get_stats", "pbk_report",
-    "pbk_comm_unique_id", "pbk_comm_init", "pbk_comm_destroy", "pbk_locality_order", "pbk_locality_order2", "pbk_light_cone", "pbk_mt_jump_window", "pbk_shard",
+    "pbk_comm_unique_id", "pbk_comm_init", "pbk_comm_destroy", "pbk_locality_order", "pbk_locality_order2", "pbk_light_cone", "pbk_host_ell", "pbk_mt_jump_window", "pbk_shard",
 ]
 
 _lib = None
@@ -102,6 +102,8 @@ def load():
     lib.pbk_shard.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.pbk_mt_jump_window.argtypes = [C.c_uint64, C.c_void_p]
     lib.pbk_locality_order.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.pbk_host_ell.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pbk_light_cone.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]
     lib.pbk_locality_order2.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]

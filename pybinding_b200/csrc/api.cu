@@ -124,6 +124,16 @@ int pbk_locality_order2(int64_t n, const int32_t* indptr, const int32_t* indices
     return PBK_OK;
 }
 
+int pbk_host_ell(int dtype, int64_t n, const int32_t* indptr, const int32_t* indices, const void* data, double min_energy,
+                 double max_energy, const int32_t* order, int32_t* k, int64_t* pitch, void* val, int32_t* col) {
+    if (n <= 0 || !indptr || !indices || !data || !k || !pitch || !(min_energy < max_energy)) return PBK_INVALID_ARGUMENT;
+    try {
+        return host_scaled_ell(dtype, n, indptr, indices, data, min_energy, max_energy, order, k, pitch, val, col);
+    } catch (...) {
+        return PBK_RUNTIME_ERROR;
+    }
+}
+
 int pbk_light_cone(int64_t n, const int32_t* indptr, const int32_t* indices, int32_t src, int32_t depth,
                    int32_t* queue, int64_t* queue_size, int32_t* borders, int32_t* num_borders, int32_t* exhausted) {
     if (n <= 0 || !indptr || !indices || src < 0 || src >= n || depth < 0 || !queue || !queue_size || !borders || !num_borders || !exhausted) {

@@ -336,6 +336,38 @@ HostEll build_ell_host(int64_t n, const int32_t* indptr, const int32_t* indices,
 
 } // anonymous namespace
 
+/// Host-only test hook (pbk_host_ell): the scaled slot-major ELL exactly as build_device_hamiltonian uploads it, for the
+/// caller's order (`order` == nullptr: create_scaled semantics) or a relabelled one (`order[new] = old`: create_reordered).
+int host_scaled_ell(int dtype, int64_t n, const int32_t* indptr, const int32_t* indices, const void* data, double min_energy,
+                    double max_energy, const int32_t* order, int32_t* k_out, int64_t* pitch_out, void* val, int32_t* col) {
+    // the energy range reaches the engine as floats (pbk_config / kpm::Config): round the same way
+    Scale const s(static_cast<float>(min_energy), static_cast<float>(max_energy));
+    std::vector<int32_t> rmap;
+    if (order) {
+        rmap.assign(static_cast<size_t>(n), -1);
+        for (int64_t i = 0; i < n; ++i) {
+            if (order[i] < 0 || order[i] >= n || rmap[order[i]] >= 0) return PBK_INVALID_ARGUMENT;   // not a permutation
+            rmap[order[i]] = static_cast<int32_t>(i);
+        }
+    }
+    const int32_t* rm = order ? rmap.data() : nullptr;
+    HostEll ell;
+    switch (dtype) {
+        case F32: ell = build_ell_host<float>(n, indptr, indices, static_cast<const float*>(data), true, s, order, rm); break;
+        case C64: ell = build_ell_host<cf>(n, indptr, indices, static_cast<const cf*>(data), true, s, order, rm); break;
+        case F64: ell = build_ell_host<double>(n, indptr, indices, static_cast<const double*>(data), true, s, order, rm); break;
+        case C128: ell = build_ell_host<cd>(n, indptr, indices, static_cast<const cd*>(data), true, s, order, rm); break;
+        default: return PBK_INVALID_ARGUMENT;
+    }
+    *k_out = ell.k;
+    *pitch_out = ell.pitch;
+    if (val && col) {
+        std::memcpy(val, ell.val, ell.val_bytes);
+        std::memcpy(col, ell.col, ell.col_count * sizeof(int32_t));
+    }
+    return PBK_OK;
+}
+
 /// Locality ordering for the stochastic (full-system) quantities: the sites are relabelled cluster by cluster,
 /// each cluster a breadth-first ball of at most `tile` sites grown from a seed on the frontier of the clusters
 /// made so far.  A CTA of the step kernel works through one tile of consecutive rows at a time, so the x-rows

@@ -330,6 +330,10 @@ private:
 /// units [first, first + count) of `total` owned by `rank` (engine.cu)
 void shard_range(int total, int world, int rank, int* first, int* count);
 
+/// host-only test hook: the scaled ELL that would be uploaded (engine.cu)
+int host_scaled_ell(int dtype, int64_t n, const int32_t* indptr, const int32_t* indices, const void* data, double min_energy,
+                    double max_energy, const int32_t* order, int32_t* k_out, int64_t* pitch_out, void* val, int32_t* col);
+
 /// truncated breadth-first walk from `src` (engine.cu); `mark` holds -1 for every site and is restored on return
 Cone light_cone(const int32_t* indptr, const int32_t* indices, int32_t src, int depth, std::vector<int32_t>& mark);
 
