@@ -15,20 +15,66 @@ import numpy as np
 from . import _lib
 from . import results
 
-__all__ = ['KPM', 'kpm', 'kpm_cuda', 'SpatialLDOS', 'Deferred',
+__all__ = ['KPM', 'kpm', 'kpm_cuda', 'SpatialLDOS', 'SiteSelection', 'Deferred',
            'jackson_kernel', 'lorentz_kernel', 'dirichlet_kernel']
 
 
+class SiteSelection:
+    """The sites a spatial LDOS was computed for: the role `system[shape.contains(...)]` (a sliced `System` /
+    `StructureMap`) plays in the reference (pybinding/chebyshev.py:223-227) for models that are not pybinding systems.
+    Holds the Hamiltonian indices and positions of the selected sites."""
+
+    def __init__(self, system, indices, data=None):
+        self.indices = np.asarray(indices, np.int64)
+        x, y, z = system.positions
+        self.x, self.y, self.z = (np.asarray(a)[self.indices] for a in (x, y, z))
+        self._system = system
+        self.data = data
+
+    def __len__(self):
+        return int(self.indices.size)
+
+    def find_nearest(self, position, sublattice=""):
+        """Position (column of the LDOS table) of the selected site closest to `position`"""
+        keep = np.arange(len(self))
+        if sublattice:
+            start, end = self._system.sublattice_range(sublattice)
+            keep = keep[(self.indices >= start) & (self.indices < end)]
+            if keep.size == 0:
+                raise IndexError("no selected site on sublattice '{}'".format(sublattice))
+        p = np.zeros(3, np.float32)
+        p[:len(position)] = np.asarray(position, np.float32)
+        d = (self.x[keep] - p[0]) ** 2 + (self.y[keep] - p[1]) ** 2 + (self.z[keep] - p[2]) ** 2
+        return int(keep[np.argmin(d)])
+
+    def with_data(self, data):
+        """A copy carrying one value per selected site (what `StructureMap.with_data` returns in the reference)"""
+        return SiteSelection(self._system, self.indices, np.asarray(data))
+
+
 class SpatialLDOS:
-    """Holds the results of :meth:`KPM.calc_spatial_ldos` (data: energy x site)"""
+    """Holds the results of :meth:`KPM.calc_spatial_ldos` (data: energy x site).
+
+    Same surface as the reference class (pybinding/chebyshev.py:20-62): a product of a `Series` and a structure map."""
 
     def __init__(self, data, energy, structure):
         self.data = data
         self.energy = energy
-        self.structure = structure  # indices of the sites inside the shape
+        self.structure = structure  # the selected sites: a sliced pybinding System, or a `SiteSelection`
+
+    def structure_map(self, energy):
+        """The LDOS of every selected site at the sampled energy closest to `energy`, attached to the structure"""
+        idx = np.argmin(abs(self.energy - energy))
+        return self.structure.with_data(self.data[idx])
+
+    def ldos(self, position, sublattice=""):
+        """The LDOS as a function of energy at the selected site closest to `position` -> :class:`Series`"""
+        idx = self.structure.find_nearest(position, sublattice)
+        return results.Series(self.energy, self.data[:, idx],
+                              labels=dict(variable="E (eV)", data="LDOS", columns="orbitals"))
 
     def ldos_at(self, energy):
-        """LDOS of every selected site at the sampled energy closest to `energy`"""
+        """LDOS of every selected site at the sampled energy closest to `energy` (plain array)"""
         idx = np.argmin(abs(self.energy - energy))
         return self.data[idx]
 
@@ -412,8 +458,13 @@ class KPM:
         ldos = self.impl.calc_spatial_ldos(energy, broadening, shape, sublattice)
         system = self.system
         contains = np.asarray(shape.contains(*system.positions))
+        if hasattr(system, "__getitem__") and hasattr(system, "sub"):   # a pybinding System: slice it like the reference does
+            smap = system[contains]
+            if sublattice:
+                smap = smap[smap.sub == sublattice]
+            return SpatialLDOS(ldos, np.asarray(energy), smap)
         start, end = system.sublattice_range(sublattice)
-        return SpatialLDOS(ldos, np.asarray(energy), start + np.flatnonzero(contains[start:end]))
+        return SpatialLDOS(ldos, np.asarray(energy), SiteSelection(system, start + np.flatnonzero(contains[start:end])))
 
     def calc_dos(self, energy, broadening, num_random=1):
         """Calculate the density of states as a function of energy -> :class:`Series`"""
