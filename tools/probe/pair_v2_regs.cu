@@ -5,7 +5,9 @@
 //   1. the f64 sums of a phase live in registers only inside that phase; between phases they are parked in (volatile) local
 //      memory -- one 96-byte store + load per tile and thread instead of 24 registers held for the whole kernel,
 //   2. the producer's cursor (tile, phase, row, ring position) lives in shared memory: only thread 0 ever reads it,
-//   3. no software prefetch of the next halo row's record (the halo rows are to be bulk-prefetched instead).
+//   3. no software prefetch of the next halo row's record; instead (PAIR_HALO_BULK=1, default) every thread bulk-copies one
+//      halo row's a-chunk and H record into shared memory at the start of the tile (own mbarrier, proxy fence after the
+//      previous tile's generic accesses), so the halo loop only waits for gathers and overwrites a with c in place.
 // `make -C tools/probe pair_v2_regs` prints ptxas' register / spill numbers for complex64, ELL width 3:
 //
 //   variant (float2, K = 3, 256 threads)         __launch_bounds__(256, 2)   (256, 3)              (256, 4)
@@ -13,10 +15,12 @@
 //   + sums parked between phases                 117                         80, 60 B               64, 200 B
 //   + no halo record prefetch                    107                         80, none               64, 184 B
 //   + producer cursor in shared memory           101                         80, none               64, 32 B
+//   + halo rows bulk-prefetched (this file)      103                         80, none               64, 44 B
 //
 // i.e. the kernel fits 3 CTAs/SM without spills and 4 CTAs/SM (the occupancy of the single-step kernel) with 32 bytes of
-// spills.  Unverified on hardware: compile-only.  Next step (round 2): move these changes into kernels_pair.cu, bulk-prefetch
-// the halo rows into the halo buffer at the start of each tile, and re-measure at R = 32 with 3 pipeline stages.
+// spills.  Unverified on hardware: compile-only (the launcher below still sizes shared memory for the round-1 layout: the
+// halo prefetch needs 8 more bytes for its barrier and `hrec_off` / halo_max * rec bytes for the staged records).
+// Next step (round 2): move these changes into kernels_pair.cu and re-measure at R = 32 with 3 pipeline stages.
 #include "bulk_common.cuh"
 
 #include <map>
@@ -36,6 +40,7 @@ struct PairDev {
     int nrows, ntiles, cpr, rpb, tile;   // tile: rows per locality cluster (any multiple of 1; block-iterations cover rpb rows)
     int R, stages;
     uint32_t rec, valoff, stage_bytes, halo_off;   // halo buffer starts halo_off bytes into dynamic shared memory
+    uint32_t hrec_off;                             // PAIR_HALO_BULK: staged H records of the halo rows start here
     double* partials; unsigned* counter; double* mom; double* m01; int M; int n;
 };
 
@@ -59,6 +64,10 @@ template<class CH> __device__ __forceinline__ void store_plain(CH* p, CH const& 
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
 }
 template<class T> __device__ __forceinline__ T ldg_val(const unsigned char* p) { return ldg_scalar(reinterpret_cast<const T*>(p)); }
+
+#ifndef PAIR_HALO_BULK
+#define PAIR_HALO_BULK 1   // 1: the halo rows' a-chunks and H records are bulk-prefetched at the start of the tile
+#endif
 
 template<class T, int V, int K, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) cheb_pair_bulk(PairDev a) {
@@ -92,6 +101,7 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_pair_bulk(PairDev a) {
 
     if (tid == 0) {
         for (uint32_t st = 0; st < S; ++st) { mbar_init(full0 + 8u * st, 1u); mbar_init(full0 + empty_off + 8u * st, TPB / 32); }
+        mbar_init(full0 + 16u * S, 1u);   // halo prefetch barrier
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -147,6 +157,7 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_pair_bulk(PairDev a) {
     for (int q = 0; q < NACC; ++q) { park1[q] = 0.0; park2[q] = 0.0; }
 
     uint32_t sb = smem0, fb = full0, cph = 0;
+    uint32_t hph = 0;   // phase of the halo prefetch barrier
     auto next_stage = [&]() {
         sb += stage_bytes; fb += 8u;
         if (sb == ring_end) { sb = smem0; fb = full0; cph ^= 1u; }
@@ -158,6 +169,22 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_pair_bulk(PairDev a) {
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         uint32_t const trows = rows_of(tile);
         uint32_t const tile_row0 = static_cast<uint32_t>(tile) * tile_rows;
+        int const hp = __ldg(a.halo_ptr + tile);
+        int const nh = __ldg(a.halo_ptr + tile + 1) - hp;
+#if PAIR_HALO_BULK
+        __syncthreads();   // every thread is done with the previous tile's halo buffer (generic-proxy reads and writes)
+        {
+            uint32_t const hbar = full0 + 16u * S;
+            uint32_t const row_bytes = cpr * 16u;
+            if (tid == 0) mbar_expect_tx(hbar, static_cast<uint32_t>(nh) * (row_bytes + a.rec));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // order the generic accesses before the async writes
+            for (int j = static_cast<int>(tid); j < nh; j += TPB) {
+                uint32_t const hrow = static_cast<uint32_t>(__ldg(a.halo_rows + hp + j));
+                bulk_g2s(halo0 + static_cast<uint32_t>(j) * row_bytes, va + hrow * cpr, row_bytes, hbar);
+                bulk_g2s(smem0 + a.hrec_off + static_cast<uint32_t>(j) * a.rec, a.packed + static_cast<size_t>(hrow) * a.rec, a.rec, hbar);
+            }
+        }
+#endif
 
         // ---- phase 1, own rows: c = H b - a, sums |b|^2 and conj(c) b ----
         {
@@ -200,22 +227,35 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_pair_bulk(PairDev a) {
 #pragma unroll
         for (int q = 0; q < NACC; ++q) park1[q] = acc1[q];
         }
+#if !PAIR_HALO_BULK
         __syncthreads();   // every thread is done with the previous tile's halo buffer
+#endif
 
         // ---- phase 1, halo rows: c into shared memory only ----
         {
-            int const hp = __ldg(a.halo_ptr + tile);
-            int const nh = __ldg(a.halo_ptr + tile + 1) - hp;
+#if PAIR_HALO_BULK
+            mbar_wait(full0 + 16u * S, hph);
+            hph ^= 1u;
+#endif
             for (int j = static_cast<int>(ty); active && j < nh; j += static_cast<int>(rpb)) {
+                int32_t c[K]; T v[K];
+#if PAIR_HALO_BULK
+                uint32_t const rp = smem0 + a.hrec_off + static_cast<uint32_t>(j) * a.rec;
+                uint32_t const my = halo0 + (static_cast<uint32_t>(j) * cpr + tx) * 16u;
+#pragma unroll
+                for (int s = 0; s < K; ++s) { c[s] = lds_i32(rp + 4u * s); lds_val(rp + a.valoff + static_cast<uint32_t>(sizeof(T)) * s, v[s]); }
+                CH const yv = lds_chunk_sync<CH>(my);   // a[halo row], overwritten in place by c below (this thread owns the chunk)
+#else
                 uint32_t const hrow = static_cast<uint32_t>(__ldg(a.halo_rows + hp + j));
                 const unsigned char* rp = a.packed + static_cast<size_t>(hrow) * a.rec;
-                int32_t c[K]; T v[K];
+                uint32_t const my = halo0 + (static_cast<uint32_t>(j) * cpr + tx) * 16u;
 #pragma unroll
                 for (int s = 0; s < K; ++s) { c[s] = __ldg(reinterpret_cast<const int32_t*>(rp) + s); v[s] = ldg_val<T>(rp + a.valoff + sizeof(T) * s); }
+                CH const yv = load_nc(va + (hrow * cpr + tx));
+#endif
                 CH xg[K];
 #pragma unroll
                 for (int s = 0; s < K; ++s) xg[s] = load_nc(vb + (static_cast<uint32_t>(c[s]) * cpr + tx));
-                CH const yv = load_nc(va + (hrow * cpr + tx));
                 CH out;
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
@@ -224,7 +264,7 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_pair_bulk(PairDev a) {
                     for (int s = 0; s < K; ++s) r = fma_(v[s], xg[s].e[e], r);
                     out.e[e] = r;
                 }
-                sts_chunk(halo0 + (static_cast<uint32_t>(j) * cpr + tx) * 16u, out);
+                sts_chunk(my, out);
             }
         }
 
