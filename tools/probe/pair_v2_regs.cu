@@ -18,9 +18,9 @@
 //   + halo rows bulk-prefetched (this file)      103                         80, none               64, 44 B
 //
 // i.e. the kernel fits 3 CTAs/SM without spills and 4 CTAs/SM (the occupancy of the single-step kernel) with 32 bytes of
-// spills.  Unverified on hardware: compile-only (the launcher below still sizes shared memory for the round-1 layout: the
-// halo prefetch needs 8 more bytes for its barrier and `hrec_off` / halo_max * rec bytes for the staged records).
-// Next step (round 2): move these changes into kernels_pair.cu and re-measure at R = 32 with 3 pipeline stages.
+// spills.  Unverified on hardware: compile-only.  The file is a drop-in candidate for kernels_pair.cu (same PairArgs / launcher
+// interface; shared memory: stage ring, barriers, halo buffer, staged halo records).
+// Next step (round 2): swap it in, run the pair parity tests, and re-measure at R = 32 with 3 pipeline stages.
 #include "bulk_common.cuh"
 
 #include <map>
@@ -378,9 +378,10 @@ cudaError_t launch_pair_t(PairArgs const& a, int num_sms, cudaStream_t stream, L
     if (a.nrows < 4 * a.tile || (a.nrows + a.tile) * cpr >= (int64_t{1} << 32) || a.nrows >= (int64_t{1} << 31) - (int64_t{1} << 24)) return cudaSuccess;
     int const stages = a.stages > 16 ? 16 : (a.stages < 2 ? 2 : a.stages);
     uint32_t const stage_bytes = 2u * PAIR_TPB * 16u + (static_cast<uint32_t>(rpb) * rec + 127u) / 128u * 128u;
-    uint32_t const halo_off = (stages * stage_bytes + 16u * stages + 127u) / 128u * 128u;
+    uint32_t const halo_off = (stages * stage_bytes + 16u * stages + 8u /* halo prefetch barrier */ + 127u) / 128u * 128u;
     int64_t const halo_bytes = static_cast<int64_t>(a.halo_max) * cpr * 16;
-    int64_t const dyn = halo_off + halo_bytes;
+    int64_t const hrec_off = halo_off + halo_bytes;                       // staged H records of the halo rows (16-byte units)
+    int64_t const dyn = hrec_off + static_cast<int64_t>(a.halo_max) * rec;
     if (dyn > PAIR_MAX_DYN) return cudaSuccess;
     // 3 resident CTAs (<= 80 registers, some spills) when their shared memory fits, else 2 (<= 128 registers)
     int minb = a.min_blocks;
@@ -401,7 +402,7 @@ cudaError_t launch_pair_t(PairArgs const& a, int num_sms, cudaStream_t stream, L
     d.halo_ptr = a.halo_ptr; d.halo_rows = a.halo_rows;
     d.a = a.a; d.b = a.b; d.c = a.c; d.d = a.d;
     d.nrows = static_cast<int>(a.nrows); d.ntiles = static_cast<int>(ntiles); d.cpr = cpr; d.rpb = rpb; d.tile = static_cast<int>(a.tile);
-    d.R = a.R; d.stages = stages; d.rec = rec; d.valoff = valoff; d.stage_bytes = stage_bytes; d.halo_off = halo_off;
+    d.R = a.R; d.stages = stages; d.rec = rec; d.valoff = valoff; d.stage_bytes = stage_bytes; d.halo_off = halo_off; d.hrec_off = static_cast<uint32_t>(hrec_off);
     d.partials = a.partials; d.counter = a.counter; d.mom = a.mom; d.m01 = a.m01; d.M = a.M; d.n = a.n;
     fn<<<grid, PAIR_TPB, static_cast<size_t>(dyn), stream>>>(d);
     *handled = true;
