@@ -114,46 +114,103 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload):
-    """dram bytes per launch of the step kernel from the committed ncu capture, or None"""
+def ncu_traffic(workload, vectors_per_pass):
+    """dram bytes per launch of the step kernel from a committed ncu capture of THIS workload at THIS number of vectors
+    per pass (profiles/traffic.json: {workload: {"<R>": bytes}}), else None -- a capture of another launch shape is not
+    a measurement of this run"""
     path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(path):
-        try:
-            return json.load(open(path)).get(workload)
-        except Exception:
-            return None
+    try:
+        entry = json.load(open(path)).get(workload)
+        if isinstance(entry, dict):
+            value = entry.get(str(int(vectors_per_pass)))
+            return float(value) if value is not None else None
+    except Exception:
+        pass
     return None
 
 
-def cpu_sample(model, w, threads, target_seconds=15.0):
-    """Reference-shaped CPU run (oracle port) on a bounded sample of the same Hamiltonian.
+TOLERANCE = {"float32": 1e-5, "complex64": 1e-5, "float64": 1e-11, "complex128": 1e-11}   # north_star, relative to max |mu|
 
-    The reference's cost is exactly linear in moments and vectors, so the sample keeps the full Hamiltonian and
-    one SIMD batch of vectors per thread and shortens the number of moments: a short calibration run sizes it
-    for about `target_seconds` of CPU work.
+
+def parity_moments(w, nnz):
+    """Number of leading moments of the timed run which are compared with the oracle: all of them when that is cheap,
+    otherwise the first 10 (the 4k + 2 number next to 8)"""
+    return w["moments"] if nnz * w["moments"] * w["vectors"] < 2e10 else 10
+
+
+class ParityOracle:
+    """The `hp` oracle (oracle/: CPU restatement of the reference, f64 accumulation) on the same Hamiltonian and the
+    same MT19937 starters, run on the host cores in a background thread while the GPU loop is being timed."""
+
+    def __init__(self, model, w, threads=0):
+        from oracle.oracle import OracleKPM, hardware_threads
+        self.count = parity_moments(w, model.hamiltonian.nnz)
+        self.vectors = w["vectors"]
+        self.threads = threads or max(1, hardware_threads() - 1)
+        self.result, self.error, self.seconds = None, None, 0.0
+        self._make = lambda: OracleKPM(model.hamiltonian, energy_range=w["energy_range"], num_threads=self.threads, hp=True)
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        t0 = time.perf_counter()
+        try:
+            self.result = self._make().dos_moments(self.count, self.vectors)
+        except Exception as e:   # reported by check()
+            self.error = e
+        self.seconds = time.perf_counter() - t0
+
+    def check(self, moments, dtype):
+        """max |gpu - oracle| / max |oracle| over the compared moments, and the verdict"""
+        self._thread.join()
+        if self.error is not None:
+            raise self.error
+        got = np.asarray(moments)[:self.count]
+        err = float(np.abs(got - self.result).max() / np.abs(self.result).max())
+        tol = TOLERANCE[np.dtype(dtype).name]
+        return dict(parity_max_rel=err, tolerance=tol, moments_compared=int(self.count), vectors=int(self.vectors),
+                    oracle="hp (f64 accumulation), identical MT19937 starters, {} host threads, {:.1f} s".format(
+                        self.threads, self.seconds), passed=bool(err <= tol))
+
+
+def cpu_sample(model, w, threads):
+    """Reference-shaped CPU run (oracle port, native accumulation) on a bounded sample of the same Hamiltonian.
+
+    One wave of thread-pool jobs (SIMD batch x threads vectors, or all vectors if fewer) runs a shortened recursion on
+    the FULL Hamiltonian with a probe around `probe_steps` recursion steps in its middle: that gives the cost per step
+    with every thread busy (the asymptotic rate) and, by difference, the fixed cost per wave (starter, allocation and
+    first touch of the vector blocks, r1).  Both are exactly linear in the reference, so the whole job is
+    waves * (fixed + (M / 2 - 1) * t_step) and `value` is nnz * M * R divided by that.
     """
     from oracle.oracle import OracleKPM, hardware_threads
     threads = threads or hardware_threads()
+    M, R = w["moments"], w["vectors"]
     batch = 32 // np.dtype(w["dtype"]).itemsize           # the reference's SIMD batch (simd.hpp:42-44)
-    vectors = min(w["vectors"], max(batch, threads * batch))
+    vectors = min(R, max(batch, threads * batch)) if R > 1 else 1
+    jobs = max(1, vectors // batch + (vectors % batch))   # Compute.cpp:52-63: batches, then single vectors
     nnz = model.hamiltonian.nnz
+    max_steps = max(2, (M // 2 - 4) // 2 * 2)
+    probe_steps = int(min(max_steps, max(2, round(1.2e11 / (2.0 * nnz * vectors) / 2) * 2)))
+    n1, n2 = 2, 2 + probe_steps
+    m_run = 2 * n2 + 2
     ref = OracleKPM(model.hamiltonian, energy_range=w["energy_range"], num_threads=threads, hp=False)
-    moments = 6
-    seconds = ref.time_dos(moments, vectors, threads, cheap_starter=True)
-    for _ in range(3):  # grow the sample until it is long enough to be dominated by the recursion
-        if seconds >= 0.5 * target_seconds or moments >= w["moments"]:
-            break
-        scale = min(8.0, target_seconds / max(seconds, 1e-9))
-        moments = int(min(w["moments"], max(moments + 4, moments * scale)))
-        moments = max(10, (moments - 2) // 4 * 4 + 2)
-        seconds = ref.time_dos(moments, vectors, threads, cheap_starter=True)
-    value = nnz * moments * vectors / seconds
-    return dict(value=value, unit=UNIT, cores=threads, kind="port",
+    total, probe, reports = ref.time_dos_probe(m_run, vectors, threads, n1, n2, cheap_starter=True)
+    t_step = probe / probe_steps
+    fixed = max(0.0, total - n2 * t_step)                 # the run has n2 steps (n = 2 .. n2 + 1)
+    waves = -(-R // vectors)
+    job_seconds = waves * (fixed + (M // 2 - 1) * t_step)
+    value = nnz * M * R / job_seconds
+    slope = 2.0 * nnz * vectors / t_step
+    return dict(value=value, unit=UNIT, cores=min(threads, jobs), kind="port",
+                asymptotic_value=slope, fixed_seconds_per_wave=fixed, seconds_per_step=t_step, sample_seconds=total,
+                extrapolated_job_seconds=job_seconds,
                 sample="{} moments x {} vectors on the full Hamiltonian ({:.1f} s): oracle C++ port of the reference "
                        "CPU path (ELL, interleaved diagonal recursion, 32-byte SIMD batches of {}, thread pool over "
-                       "batches); recursion only -- the reference's mutex-serialised MT19937 starter is replaced by "
-                       "a trivial fill for this short sample, which favours the CPU".format(
-                           moments, vectors, seconds, batch)), seconds, moments, vectors
+                       "batches, native accumulation); {} recursion steps timed with all {} jobs running: {:.3f} s per "
+                       "step = {:.3e} units/s asymptotically; fixed cost per wave {:.1f} s (with a trivial +-1 fill "
+                       "instead of the reference's mutex-serialised MT19937 starter, i.e. a lower bound); value = the "
+                       "whole job ({} moments x {} vectors, {} wave(s)) extrapolated linearly".format(
+                           m_run, vectors, total, batch, probe_steps, reports, t_step, slope, fixed, M, R, waves)), total
 
 
 def run_reference(args, w):
@@ -161,18 +218,19 @@ def run_reference(args, w):
     if rank != 0:
         return
     model = build_model(w)
-    steps = []
-    base = None
-    for i in range(args.warmup + args.steps):
-        base, seconds, moments, vectors = cpu_sample(model, w, 0)
-        if i >= args.warmup:
-            steps.append((seconds, base["value"]))
-    value = float(np.mean([v for _, v in steps]))
-    base["value"] = value
+    # the arm is a bounded CPU sample: at most two of them whatever --steps / --warmup say (the first one is the
+    # warm-up when there are two), so that the arm ends within a few minutes
+    samples = max(1, min(2, args.warmup + args.steps))
+    base, seconds = None, 0.0
+    for _ in range(samples):
+        base, seconds = cpu_sample(model, w, 0)
+    value = base["value"]
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-               ms_per_step=float(np.mean([s for s, _ in steps]) * 1e3), higher_is_better=True, scaling="strong",
+               ms_per_step=seconds * 1e3, higher_is_better=True, scaling="strong",
                vs_baseline=None, dtype=w["dtype"], data="synthetic", impl="reference",
-               config=dict(workload=w["text"], note="CPU sample extrapolates linearly in moments and vectors"),
+               config=dict(workload=w["text"], samples_run=samples,
+                           note="bounded CPU sample on the full Hamiltonian, extrapolated linearly in moments and vectors "
+                                "(see cpu_baseline.sample); ms_per_step is the duration of one sample"),
                cpu_baseline=base,
                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(out)
@@ -210,6 +268,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison (sweeps only: the line says so)")
     ap.add_argument("--max-batch", type=int, default=0)
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -253,6 +312,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # parity gate: the oracle computes the leading moments of the very run that is timed (same H, same starters) on the
+    # host cores meanwhile; the line is only printed when they agree
+    oracle = ParityOracle(model, w) if (rank == 0 and not args.no_parity) else None
     kpm = make_kpm()
     kpm.impl.scaling_factors  # bounds known (explicit range): nothing to compute
     # ---- device-resident timing: Hamiltonian already in HBM, one step = the whole moments phase ----
@@ -282,12 +344,13 @@ def main():
     clocks = sampler.stop()
     t_step = float(np.mean(step_times))
     value = nnz * M * R / t_step
+    parity = oracle.check(moments, w["dtype"]) if oracle else None   # joins the oracle thread before the e2e leg
 
     peak, peak_src = measured_peak()
     achieved = (step_bytes / step_launches) / (step_ms / step_launches * 1e-3) / 1e9 if step_launches else 0.0
     s_item = np.dtype(w["dtype"]).itemsize
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                    traffic=ncu_traffic(args.workload), peak_source=peak_src,
+                    traffic=ncu_traffic(args.workload, batch), peak_source=peak_src,
                     kernel="cheb_step_bulk (fused SpMM + moments, operands staged by cp.async.bulk)" if bulk_launches
                     else "cheb_step (fused SpMM + moments)", staged_launches=int(bulk_launches),
                     algorithmic_bytes_per_launch=step_bytes / max(step_launches, 1),
@@ -324,6 +387,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:   # the CPU baseline is reported at N = 1 only
         cpu = cpu_sample(model, w, 0)[0]
 
+    if rank == 0 and parity is not None and not parity["passed"]:
+        sys.stderr.write("bench.py: PARITY FAILED -- the first {moments_compared} moments of the timed run differ from the "
+                         "oracle by {parity_max_rel:.3e} (tolerance {tolerance:.0e}); no result line is printed\n".format(**parity))
+        emit(dict(metric=METRIC, value=None, unit=UNIT, n_gpus=world, error="parity failed", parity=parity))
+        if world > 1:
+            dist.destroy_process_group()
+        sys.exit(1)
     if rank == 0:
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                    ms_per_step=t_step * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None,
@@ -336,6 +406,7 @@ def main():
                                wall_ms_per_step=float(np.mean(wall_times)) * 1e3,
                                timing="CUDA events on the engine stream around the whole moments phase, max over ranks"),
                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
+                   parity=parity, parity_max_rel=parity["parity_max_rel"] if parity else None,
                    moment_checksum=float(np.abs(moments).sum()))
         emit(out)
     if world > 1:

@@ -498,8 +498,21 @@ template<class T, int B> std::vector<T> make_r1(Ell<T> const& h2, std::vector<T>
 // ------------------------------------------------------------------------------------------------
 // Collectors (src/kpm/default/collectors.cpp:6-106)
 // ------------------------------------------------------------------------------------------------
+/// Timing aid of bench.py's cpu_baseline (not part of the reference): wall time a job spends between recursion steps
+/// n1 and n2, so that a bounded sample reports the asymptotic cost per moment without the per-vector fixed cost
+/// (starter generation, allocation and first touch of the vector blocks, r1 = H r0 / 2).
+struct StepProbe {
+    int n1 = 0, n2 = 0;
+    std::mutex mutex;
+    double max_elapsed = 0;   // slowest job: all jobs of one wave run concurrently
+    int reports = 0;
+    void report(double seconds) { std::lock_guard<std::mutex> lk(mutex); max_elapsed = std::max(max_elapsed, seconds); ++reports; }
+};
+
 template<class T, class A, int B> struct DiagonalCollector {  // B == 1: DiagonalCollector, else Batch
     static constexpr bool diagonal = true;
+    StepProbe* probe = nullptr;
+    std::chrono::steady_clock::time_point probe_t0;
     int num_moments;
     std::vector<A> moments;  // num_moments x B, row-major
     A m0[B], m1[B];
@@ -518,6 +531,10 @@ template<class T, class A, int B> struct DiagonalCollector {  // B == 1: Diagona
         }
     }
     void operator()(int n, A const* m2, A const* m3) {
+        if (probe) {
+            if (n == probe->n1) probe_t0 = std::chrono::steady_clock::now();
+            else if (n == probe->n2) probe->report(std::chrono::duration<double>(std::chrono::steady_clock::now() - probe_t0).count());
+        }
         for (int j = 0; j < B; ++j) {
             moments[static_cast<size_t>(2 * (n - 1)) * B + j] = A{2} * (m2[j] - m0[j]);
             moments[static_cast<size_t>(2 * (n - 1) + 1) * B + j] = A{2} * m3[j] - m1[j];
@@ -676,6 +693,13 @@ void offdiagonal_interleaved(OffDiagonalCollector<T>& collect, std::vector<T> r0
 // ------------------------------------------------------------------------------------------------
 template<class T> struct Starter {
     std::function<std::vector<T>()> make;
+    // Optional split of `make` for starters that consume a shared random stream: `draw` takes the next vector's worth
+    // of uniform reals and must run under the mutex (the stream order defines which vector gets which numbers, exactly as
+    // in the reference where all of `make` runs under Starter::mutex, Starter.hpp:18-21); `finish` turns them into the
+    // starter vector and may run concurrently.  Same values as `make`, only less serialised -- an oracle-side speed-up
+    // for checks at benchmark size (tens of millions of sites x 64 vectors).
+    std::function<std::vector<real_of<T>>()> draw;
+    std::function<std::vector<T>(std::vector<real_of<T>> const&)> finish;
     int vector_size = 0;
     int count = 0;
     std::unique_ptr<std::mutex> mutex = std::make_unique<std::mutex>();
@@ -693,10 +717,11 @@ template<class T> struct RandomStarterFn {
     Csr<T> op;  // applied in the original ordering, before the reorder
     std::shared_ptr<std::mt19937> generator = std::make_shared<std::mt19937>();
 
-    std::vector<T> operator()() {
+    std::vector<T> operator()() { return finish(draw()); }
+    std::vector<real_of<T>> draw() { return make_random_real<real_of<T>>(oh->size(), *generator); }
+    std::vector<T> finish(std::vector<real_of<T>> const& u) const {
         using R = real_of<T>;
         std::vector<T> r0(oh->size());
-        auto const u = make_random_real<R>(oh->size(), *generator);
         if constexpr (!traits<T>::cplx) {
             for (size_t i = 0; i < r0.size(); ++i) r0[i] = (u[i] < 0.5f) ? R{-1.f} : R{1.f};
         } else {
@@ -708,6 +733,24 @@ template<class T> struct RandomStarterFn {
         return r0;
     }
 };
+
+/// make_r0 for split starters: the draws happen under the caller's lock, the rest outside (see Starter::draw)
+template<class T, int B> std::vector<std::vector<real_of<T>>> draw_r0(Starter<T>& starter) {
+    starter.count += B;
+    std::vector<std::vector<real_of<T>>> u(B);
+    for (int j = 0; j < B; ++j) u[j] = starter.draw();
+    return u;
+}
+template<class T, int B> std::vector<T> finish_r0(Starter<T> const& starter, std::vector<std::vector<real_of<T>>>& u) {
+    if (B == 1) return starter.finish(u[0]);
+    std::vector<T> r0(static_cast<size_t>(starter.vector_size) * B);
+    for (int j = 0; j < B; ++j) {
+        auto const col = starter.finish(u[j]);
+        std::vector<real_of<T>>().swap(u[j]);
+        for (int i = 0; i < starter.vector_size; ++i) r0[static_cast<size_t>(i) * B + j] = col[i];
+    }
+    return r0;
+}
 
 template<class T, int B> std::vector<T> make_r0(Starter<T>& starter) {
     if (B == 1) { ++starter.count; return starter.make(); }
@@ -1015,6 +1058,7 @@ struct CoreBase {
     virtual void calc_conductivity(float const* left, float const* right, double const* mu, int nmu, double broadening,
                                    double temperature, int num_random, int num_points, cd* out) = 0;
     virtual double time_dos_steps(int num_moments, int num_random, int num_threads, bool cheap_starter) = 0;
+    StepProbe* step_probe = nullptr;   // set for the duration of a timed run (bench.py cpu_baseline)
 };
 
 template<class T, bool HP> struct Core : CoreBase {
@@ -1061,10 +1105,20 @@ template<class T, bool HP> struct Core : CoreBase {
     template<int B, class Collector>
     int with(Collector& collect, Starter<T>& starter, bool opt_size) {
         ftz_guard guard;
-        starter.mutex->lock();
-        auto const idx = starter.count;
-        auto r0 = make_r0<T, B>(starter);
-        starter.mutex->unlock();
+        int idx = 0;
+        std::vector<T> r0;
+        if (starter.draw && starter.finish) {
+            starter.mutex->lock();
+            idx = starter.count;
+            auto u = draw_r0<T, B>(starter);
+            starter.mutex->unlock();
+            r0 = finish_r0<T, B>(starter, u);
+        } else {
+            starter.mutex->lock();
+            idx = starter.count;
+            r0 = make_r0<T, B>(starter);
+            starter.mutex->unlock();
+        }
         std::vector<T> r1 = oh.use_ell ? make_r1<T, B>(oh.ell, r0) : make_r1<T, B>(oh.csr, r0);
         collect.initial(r0, r1);
         run<B>(collect, std::move(r0), std::move(r1), opt_size);
@@ -1126,6 +1180,7 @@ template<class T, bool HP> struct Core : CoreBase {
         for (int i = 0; i < num_batches; ++i) {
             jobs.emplace_back([&] {
                 DiagonalCollector<T, A, B> collect(num_moments);
+                collect.probe = step_probe;
                 auto const idx = with<B>(collect, starter, opt_size);
                 add(collect.moments, B, idx);
             });
@@ -1133,6 +1188,7 @@ template<class T, bool HP> struct Core : CoreBase {
         for (int i = 0; i < num_singles; ++i) {
             jobs.emplace_back([&] {
                 DiagonalCollector<T, A, 1> collect(num_moments);
+                collect.probe = step_probe;
                 auto const idx = with<1>(collect, starter, opt_size);
                 add(collect.moments, 1, idx);
             });
@@ -1147,7 +1203,10 @@ template<class T, bool HP> struct Core : CoreBase {
     Starter<T> random_starter(Csr<T> op = {}) {
         Starter<T> s;
         s.vector_size = oh.size();
-        s.make = RandomStarterFn<T>{&oh, std::move(op)};
+        auto fn = std::make_shared<RandomStarterFn<T>>(RandomStarterFn<T>{&oh, std::move(op)});
+        s.make = [fn] { return (*fn)(); };
+        s.draw = [fn] { return fn->draw(); };
+        s.finish = [fn](std::vector<real_of<T>> const& u) { return fn->finish(u); };
         return s;
     }
     Starter<T> unit_starter() {
@@ -1367,6 +1426,7 @@ template<class T, bool HP> struct Core : CoreBase {
             // dominate a run with few moments.  The recursion cost does not depend on the values.
             auto state = std::make_shared<uint64_t>(0x9E3779B97F4A7C15ull);
             int const size = oh.size();
+            starter.draw = nullptr; starter.finish = nullptr;
             starter.make = [state, size]() {
                 std::vector<T> r0(size);
                 uint64_t x = *state;
@@ -1492,6 +1552,18 @@ int orc_last_num_moments(void* p) { return static_cast<CoreBase*>(p)->last_num_m
 double orc_moments_seconds(void* p) { return static_cast<CoreBase*>(p)->moments_seconds; }
 int orc_time_dos(void* p, int M, int num_random, int num_threads, int cheap_starter, double* seconds) { ORC_TRY
     *seconds = static_cast<CoreBase*>(p)->time_dos_steps(M, num_random, num_threads, cheap_starter != 0); ORC_CATCH }
+/// Same run with a probe around recursion steps [n1, n2) (collector calls n1 .. n2 of calc_moments' diagonal loop, each
+/// step = 2 moments): out[0] = seconds of the whole moments phase (what the reference's moments_timer covers),
+/// out[1] = seconds the slowest job spent between the two steps, out[2] = jobs that reported.
+int orc_time_dos_probe(void* p, int M, int num_random, int num_threads, int cheap_starter, int n1, int n2, double* out) { ORC_TRY
+    auto* core = static_cast<CoreBase*>(p);
+    StepProbe probe;
+    probe.n1 = n1; probe.n2 = n2;
+    core->step_probe = &probe;
+    try { out[0] = core->time_dos_steps(M, num_random, num_threads, cheap_starter != 0); }
+    catch (...) { core->step_probe = nullptr; throw; }
+    core->step_probe = nullptr;
+    out[1] = probe.max_elapsed; out[2] = probe.reports; ORC_CATCH }
 int orc_hardware_threads() { return static_cast<int>(std::thread::hardware_concurrency()); }
 
 } // extern "C"

@@ -46,7 +46,8 @@ def lib():
         for name in ("orc_bounds", "orc_required_num_moments", "orc_optimize_for", "orc_oh_get", "orc_oh_matrix",
                      "orc_oh_slice_index", "orc_random_vectors", "orc_dos_moments", "orc_ldos_moments",
                      "orc_greens_moments", "orc_kubo_moments", "orc_moments", "orc_calc_dos", "orc_calc_ldos",
-                     "orc_calc_greens", "orc_calc_conductivity", "orc_last_num_moments", "orc_time_dos"):
+                     "orc_calc_greens", "orc_calc_conductivity", "orc_last_num_moments", "orc_time_dos",
+                     "orc_time_dos_probe"):
             getattr(_lib, name).restype = C.c_int
     return _lib
 
@@ -248,3 +249,15 @@ class OracleKPM:
         t = C.c_double(0)
         _check(lib().orc_time_dos(self.handle, num_moments, num_random, num_threads, int(cheap_starter), C.byref(t)))
         return t.value
+
+    def time_dos_probe(self, num_moments, num_random, num_threads, n1, n2, cheap_starter=False):
+        """One reference-shaped DOS moment run with a probe around recursion steps n1 .. n2 (2 moments per step).
+
+        Returns (total_seconds, probe_seconds, jobs): total = the whole moments phase including the per-vector fixed cost
+        (starters, allocation / first touch of the vector blocks, r1); probe = wall time of the slowest thread-pool job
+        between the two steps, i.e. the asymptotic cost of 2 * (n2 - n1) moments for all `num_random` vectors when
+        the jobs run as one wave (num_random <= num_threads * SIMD batch)."""
+        out = np.zeros(3)
+        _check(lib().orc_time_dos_probe(self.handle, num_moments, num_random, num_threads, int(cheap_starter),
+                                        int(n1), int(n2), _p(out)))
+        return float(out[0]), float(out[1]), int(out[2])

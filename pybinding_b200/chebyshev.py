@@ -16,7 +16,32 @@ from . import _lib
 from . import results
 
 __all__ = ['KPM', 'kpm', 'kpm_cuda', 'SpatialLDOS', 'SiteSelection', 'Deferred',
-           'jackson_kernel', 'lorentz_kernel', 'dirichlet_kernel']
+           'jackson_kernel', 'lorentz_kernel', 'dirichlet_kernel', 'sublattice_range']
+
+
+def sublattice_range(system, sublattice=""):
+    """`System::sublattice_range` (cppcore/src/system/System.cpp:50-66): the contiguous block of sites of one sublattice
+
+    The reference does not expose this method to Python (cppmodule/src/system.cpp:84-94), so for a real `pb.System`
+    the block is read off `system.sublattices` (site IDs, sublattice-major order; an `AliasArray` that compares with
+    names).  Systems which do provide `sublattice_range` (pybinding_b200.synthetic.System) are asked directly.
+    """
+    if hasattr(system, "sublattice_range"):
+        start, end = system.sublattice_range(sublattice)
+        return int(start), int(end)
+    num_sites = int(getattr(system, "num_sites", len(np.asarray(system.positions[0]))))
+    if not sublattice:
+        return 0, num_sites
+    ids = np.asarray(system.sublattices == sublattice)
+    if ids.shape == ():   # a plain id array compared with a name: look the name up in the lattice
+        names = getattr(getattr(system, "lattice", None), "sublattices", {})
+        if sublattice not in names:
+            raise IndexError("There is no sublattice named '{}'".format(sublattice))
+        ids = np.asarray(system.sublattices) == getattr(names[sublattice], "alias_id", names[sublattice])
+    hits = np.flatnonzero(ids)
+    if hits.size == 0:
+        raise IndexError("There is no sublattice named '{}'".format(sublattice))
+    return int(hits[0]), int(hits[-1]) + 1
 
 
 class SiteSelection:
@@ -38,7 +63,7 @@ class SiteSelection:
         """Position (column of the LDOS table) of the selected site closest to `position`"""
         keep = np.arange(len(self))
         if sublattice:
-            start, end = self._system.sublattice_range(sublattice)
+            start, end = sublattice_range(self._system, sublattice)
             keep = keep[(self.indices >= start) & (self.indices < end)]
             if keep.size == 0:
                 raise IndexError("no selected site on sublattice '{}'".format(sublattice))
@@ -353,7 +378,7 @@ class _CudaImpl:
             raise RuntimeError("This function doesn't currently support multi-orbital models")
         system = self._model.system
         contains = np.asarray(shape.contains(*system.positions))
-        start, end = system.sublattice_range(sublattice)
+        start, end = sublattice_range(system, sublattice)
         indices = start + np.flatnonzero(contains[start:end])
         return self._ldos_indices(indices, energy, broadening)
 
@@ -463,7 +488,7 @@ class KPM:
             if sublattice:
                 smap = smap[smap.sub == sublattice]
             return SpatialLDOS(ldos, np.asarray(energy), smap)
-        start, end = system.sublattice_range(sublattice)
+        start, end = sublattice_range(system, sublattice)
         return SpatialLDOS(ldos, np.asarray(energy), SiteSelection(system, start + np.flatnonzero(contains[start:end])))
 
     def calc_dos(self, energy, broadening, num_random=1):

@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <exception>
 #include <thread>
 
 namespace pbk {
@@ -62,20 +63,64 @@ static double now_seconds() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-template<class F> static void parallel_rows(int64_t n, F fn, int64_t min_items = int64_t{1} << 16) {
-    int nt = static_cast<int>(std::thread::hardware_concurrency());
-    if (nt < 1) nt = 1;
-    if (nt > 16) nt = 16;
-    if (n < min_items) nt = 1;
-    if (nt == 1) { fn(int64_t{0}, n); return; }
+/// Runs `fn(t)` on `nt` threads and joins them all before returning, also when one of them (or the thread creation
+/// itself) throws: the first exception is re-thrown on the caller's thread after the join, so nothing ever unwinds
+/// past a joinable std::thread (which would std::terminate the process across the C ABI).
+template<class F> static void run_pool(int nt, F fn) {
+    if (nt <= 1) { fn(0); return; }
     std::vector<std::thread> threads;
-    int64_t const chunk = (n + nt - 1) / nt;
-    for (int t = 0; t < nt; ++t) {
-        int64_t const b = t * chunk, e = std::min<int64_t>(n, b + chunk);
-        if (b < e) threads.emplace_back([=] { fn(b, e); });
+    std::exception_ptr error;
+    std::mutex error_mutex;
+    auto guarded = [&](int t) {
+        try { fn(t); }
+        catch (...) { std::lock_guard<std::mutex> lk(error_mutex); if (!error) error = std::current_exception(); }
+    };
+    try {
+        threads.reserve(static_cast<size_t>(nt));
+        for (int t = 0; t < nt; ++t) threads.emplace_back(guarded, t);
+    } catch (...) {
+        std::lock_guard<std::mutex> lk(error_mutex);
+        if (!error) error = std::current_exception();
     }
     for (auto& t : threads) t.join();
+    if (error) std::rethrow_exception(error);
 }
+
+static int host_threads() {
+    int nt = static_cast<int>(std::thread::hardware_concurrency());
+    return std::max(1, std::min(nt, 16));
+}
+
+template<class F> static void parallel_rows(int64_t n, F fn, int64_t min_items = int64_t{1} << 16) {
+    int nt = host_threads();
+    if (n < min_items) nt = 1;
+    if (nt == 1) { fn(int64_t{0}, n); return; }
+    int64_t const chunk = (n + nt - 1) / nt;
+    run_pool(nt, [&](int t) {
+        int64_t const b = t * chunk, e = std::min<int64_t>(n, b + chunk);
+        if (b < e) fn(b, e);
+    });
+}
+
+/// A std::thread that is always joined when the scope ends; an exception thrown by its body is kept and re-thrown by
+/// join_and_rethrow() on the owner's thread.
+class ScopedThread {
+public:
+    ScopedThread() = default;
+    template<class F> explicit ScopedThread(F fn) {
+        thread = std::thread([this, fn]() mutable { try { fn(); } catch (...) { error = std::current_exception(); } });
+    }
+    ScopedThread(ScopedThread const&) = delete;
+    ScopedThread& operator=(ScopedThread const&) = delete;
+    ~ScopedThread() { if (thread.joinable()) thread.join(); }
+    void join_and_rethrow() {
+        if (thread.joinable()) thread.join();
+        if (error) { auto e = error; error = nullptr; std::rethrow_exception(e); }
+    }
+private:
+    std::thread thread;
+    std::exception_ptr error;
+};
 
 // ------------------------------------------------------------------------------------------------
 // Scale, SliceMap, kernels
@@ -173,7 +218,8 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     PBK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (cudaEvent_t* e : {&ev0, &ev1, &ev2, &ev3, &ev_begin, &ev_end}) PBK_CUDA(cudaEventCreate(e));
     counter.alloc(64);
-    PBK_CUDA(cudaMemset(counter.as(), 0, 64));
+    PBK_CUDA(cudaMemsetAsync(counter.as(), 0, 64, stream));
+    PBK_CUDA(cudaStreamSynchronize(stream));
     mt_state.alloc(sizeof(uint32_t) * (MT_N + 8));
 }
 
@@ -205,10 +251,10 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
     // the locality ordering of the full-system layout only needs the sparsity pattern: it runs on the caller's arrays in
     // a second thread while this one copies them (parallel first touch)
     cluster_queue.clear(); cluster_rmap.clear(); cluster_tile = 0;
-    std::thread ordering;
+    std::unique_ptr<ScopedThread> ordering;   // joined on every exit path, exceptions of its body re-thrown after the join
     if (locality_tile > 0 && !identity_order) {
         cluster_tile = locality_tile;
-        ordering = std::thread([this, n_, indptr, indices] { cluster_order(n_, indptr, indices, cluster_tile, cluster_queue, cluster_rmap, macro_tiles, coarse_sites); });
+        ordering = std::make_unique<ScopedThread>([this, n_, indptr, indices] { cluster_order(n_, indptr, indices, cluster_tile, cluster_queue, cluster_rmap, macro_tiles, coarse_sites); });
     }
     h_indptr.resize_uninit(static_cast<size_t>(n) + 1);
     h_indices.resize_uninit(static_cast<size_t>(nnz));
@@ -220,7 +266,7 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
         std::memcpy(h_data.data() + b * sz, static_cast<const char*>(data) + b * sz, sz * static_cast<size_t>(e - b));
     });
     double const t_copy = now_seconds();
-    if (ordering.joinable()) ordering.join();
+    if (ordering) ordering->join_and_rethrow();
     if (std::getenv("PBK_TIMING")) std::fprintf(stderr, "[pbkpm] set_hamiltonian: copy %.3f s, + wait for the ordering %.3f s\n", t_copy - t_set0, now_seconds() - t_copy);
     has_h = true;
     clear_graphs();
@@ -566,12 +612,8 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
             }
         }
     };
-    int nt = static_cast<int>(std::thread::hardware_concurrency());
-    nt = std::max(1, std::min(nt, 16));
-    std::vector<std::thread> pool;
     std::atomic<int64_t> next{0};
-    for (int t = 0; t < nt; ++t) pool.emplace_back([&] { for (int64_t m = next++; m < nblocks; m = next++) order_block(m); });
-    for (auto& th : pool) th.join();
+    run_pool(host_threads(), [&](int) { for (int64_t m = next++; m < nblocks; m = next++) order_block(m); });
     mark("clusters inside blocks");
 }
 
@@ -824,8 +866,9 @@ void Engine::upload_operator(DeviceHamiltonian& dh, const float* pos, DeviceHami
     dh.tile = like.tile;
     dh.val.alloc(ell.val_bytes);
     dh.col.alloc(ell.col_count * sizeof(int32_t));
-    PBK_CUDA(cudaMemcpy(dh.val.as(), ell.val, ell.val_bytes, cudaMemcpyHostToDevice));
-    PBK_CUDA(cudaMemcpy(dh.col.as(), ell.col, ell.col_count * sizeof(int32_t), cudaMemcpyHostToDevice));
+    PBK_CUDA(cudaMemcpyAsync(dh.val.as(), ell.val, ell.val_bytes, cudaMemcpyHostToDevice, stream));
+    PBK_CUDA(cudaMemcpyAsync(dh.col.as(), ell.col, ell.col_count * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    PBK_CUDA(cudaStreamSynchronize(stream));   // `ell` (pageable host memory) goes out of scope with this function
     stats.h2d_bytes += static_cast<int64_t>(ell.val_bytes + ell.col_count * sizeof(int32_t));
     dh.ell = EllDev{dh.val.as(), dh.col.as<int32_t>(), n, ell.pitch, ell.k};
     dh.map.data = {static_cast<int32_t>(n)};
@@ -852,8 +895,9 @@ void Engine::upload_csr_operator(DeviceHamiltonian& dh, int64_t rows, const int3
     dh.tile = like.tile;
     dh.val.alloc(ell.val_bytes);
     dh.col.alloc(ell.col_count * sizeof(int32_t));
-    PBK_CUDA(cudaMemcpy(dh.val.as(), ell.val, ell.val_bytes, cudaMemcpyHostToDevice));
-    PBK_CUDA(cudaMemcpy(dh.col.as(), ell.col, ell.col_count * sizeof(int32_t), cudaMemcpyHostToDevice));
+    PBK_CUDA(cudaMemcpyAsync(dh.val.as(), ell.val, ell.val_bytes, cudaMemcpyHostToDevice, stream));
+    PBK_CUDA(cudaMemcpyAsync(dh.col.as(), ell.col, ell.col_count * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    PBK_CUDA(cudaStreamSynchronize(stream));   // `ell` (pageable host memory) goes out of scope with this function
     stats.h2d_bytes += static_cast<int64_t>(ell.val_bytes + ell.col_count * sizeof(int32_t));
     dh.ell = EllDev{dh.val.as(), dh.col.as<int32_t>(), rows, ell.pitch, ell.k};
     dh.map.data = {static_cast<int32_t>(rows)};
@@ -995,9 +1039,13 @@ int Engine::pick_batch(int vectors, int extra_blocks) const {
     cap = std::min(cap, config.max_batch > 0 ? config.max_batch : 64);
     if (pair_mode && pair_max_r > 0) cap = std::min(cap, pair_max_r);
     if (cap < 1) throw Error(PBK_RUNTIME_ERROR, "pbkpm: not enough device memory for one KPM vector pair");
+    // a pass of more than one vector is padded to whole 16-byte chunks (lane_pad), so the batch itself must be a
+    // multiple of the chunk width: buffers are sized for `rb` lanes and every launch uses lane_pad(lanes) <= rb
+    int const vmax = 16 / dtype_size(dtype);
+    cap = cap >= vmax ? cap / vmax * vmax : 1;
     int const nb = (vectors + cap - 1) / cap;
     int rb = (vectors + nb - 1) / nb;
-    rb = std::min(lane_pad(rb), std::max(cap, 1));
+    rb = std::min(lane_pad(rb), cap);
     return std::max(rb, 1);
 }
 
@@ -1494,17 +1542,13 @@ bool Engine::moments_ldos_cones(int M, Indices const& target, cd* out) {
         int const nc = std::min(group, count - c0);
         std::vector<Cone> cones(nc);
         {   // host: the balls of this group, one thread per site (overlaps the device work of the previous group)
-            std::vector<std::thread> pool;
             int const nt = std::min(nthreads, nc);
-            for (int t = 0; t < nt; ++t) {
-                pool.emplace_back([&, t] {
-                    for (int j = t; j < nc; j += nt) {
-                        if (first + c0 + j == 0) cones[j] = first_cone;
-                        else cones[j] = bfs_cone(target.src[first + c0 + j], depth, marks[t]);
-                    }
-                });
-            }
-            for (auto& th : pool) th.join();
+            run_pool(nt, [&](int t) {
+                for (int j = t; j < nc; j += nt) {
+                    if (first + c0 + j == 0) cones[j] = first_cone;
+                    else cones[j] = bfs_cone(target.src[first + c0 + j], depth, marks[t]);
+                }
+            });
         }
         // pooled buffers of the group
         std::vector<int64_t> ell_off(nc + 1, 0), vec_off(nc + 1, 0);
@@ -1683,6 +1727,9 @@ void Engine::moments_ldos(int M, const int32_t* idx, int nidx, cd* out) {
 void Engine::moments_greens(int M, int row, const int32_t* cols, int ncols, cd* out) {
     check_num_moments(M);
     if (ncols < 1) throw Error(PBK_INVALID_ARGUMENT, "at least one column index is required");
+    require_hamiltonian();
+    if (row < 0 || row >= n) throw Error(PBK_LOGIC_ERROR, "KPM::calc_greens(i,j): invalid value for i or j.");   // KPM.cpp:105-107
+    for (int i = 0; i < ncols; ++i) if (cols[i] < 0 || cols[i] >= n) throw Error(PBK_LOGIC_ERROR, "KPM::calc_greens(i,j): invalid value for i or j.");
     Indices target{{row}, std::vector<int32_t>(cols, cols + ncols)};
     auto& h = optimized_for(target);
     bool const opt = config.optimal_size != 0 && h.sliced;

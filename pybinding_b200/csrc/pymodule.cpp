@@ -7,7 +7,9 @@
 //
 // The model is duck-typed exactly like cpb::KPM reads it: `model.hamiltonian` (scipy CSR: f32 / c64 / f64 / c128,
 // cppmodule/src/model.cpp:29-31), `model.system.{find_nearest, to_hamiltonian_indices, positions, expanded_positions,
-// sublattice_range}` (cppmodule/src/system.cpp:85-94), `model.eval()`, `model.is_multiorbital`.
+// expanded_positions}` (cppmodule/src/system.cpp:85-94), `model.eval()`, `model.is_multiorbital`.  The sublattice range of
+// calc_spatial_ldos (System::sublattice_range, cppcore/src/system/System.cpp:50-66, not bound by the reference) comes from
+// `pybinding_b200.chebyshev.sublattice_range`, which reads `system.sublattices` on a real pybinding System.
 #include <pybind11/pybind11.h>
 #include <pybind11/functional.h>
 #include <pybind11/numpy.h>
@@ -16,6 +18,7 @@
 #include <complex>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -72,7 +75,9 @@ Kernel kernel_from_object(py::object const& k) {
 
 struct Stats {  // kpm::Stats as exposed by cppmodule/src/kpm.cpp:50-66, plus the GPU counters of pbk_stats
     pbk_stats s{};
-    double ops() const { return s.moments_time > 0 ? s.multiplier * (static_cast<double>(s.opt_nnz) + static_cast<double>(s.opt_vec)) / s.moments_time : 0.0; }
+    // Stats::ops (cppcore/src/kpm/Stats.cpp:53-58): 2 operations per non-zero, 5 per vector element; same formula as
+    // pybinding_b200.chebyshev.KPMStats.ops
+    double ops() const { return s.moments_time > 0 ? s.multiplier * (2.0 * static_cast<double>(s.nnz) + 5.0 * static_cast<double>(s.vec)) / s.moments_time : 0.0; }
 };
 
 // ---- the KPM object --------------------------------------------------------------------------------------
@@ -247,7 +252,7 @@ public:
         py::object np = py::module_::import("numpy");
         py::object pos = sys.attr("positions");
         py::object contains = np.attr("asarray")(shape.attr("contains")(pos.attr("x"), pos.attr("y"), pos.attr("z")));
-        auto const range = sys.attr("sublattice_range")(sublattice).cast<std::pair<int64_t, int64_t>>();
+        auto const range = py::module_::import("pybinding_b200.chebyshev").attr("sublattice_range")(sys, sublattice).cast<std::pair<int64_t, int64_t>>();
         auto const mask = carray<bool>(contains);
         std::vector<int32_t> idx;
         for (int64_t i = range.first; i < range.second; ++i) if (mask.data()[i]) idx.push_back(static_cast<int32_t>(i));
@@ -288,14 +293,16 @@ public:
         return out;
     }
 
+    // both take the context's mutex, which a calculation running on another thread holds while its progress callback
+    // waits for the GIL: never wait for that mutex with the GIL held
     std::string report(bool shortform) {
         std::vector<char> buf(4096);
-        check(pbk_report(ctx, shortform, buf.data(), static_cast<int64_t>(buf.size())), ctx);
+        { py::gil_scoped_release nogil; check(pbk_report(ctx, shortform, buf.data(), static_cast<int64_t>(buf.size())), ctx); }
         return buf.data();
     }
     Stats stats() {
         Stats s;
-        check(pbk_get_stats(ctx, &s.s), ctx);
+        { py::gil_scoped_release nogil; check(pbk_get_stats(ctx, &s.s), ctx); }
         return s;
     }
 
@@ -327,12 +334,19 @@ private:
 class DeferredLdos {
 public:
     DeferredLdos(py::object solver_, std::function<py::object()> fn_) : solver(std::move(solver_)), fn(std::move(fn_)) {}
-    void compute() { if (!done) { value = fn(); done = true; } }
+    // one computation even when several threads ask: the first caller runs the job, the others wait for it with the
+    // GIL released (the job itself needs the GIL to enter calc_ldos)
+    void compute() {
+        std::unique_lock<std::mutex> lock(mutex, std::defer_lock);
+        { py::gil_scoped_release nogil; lock.lock(); }
+        if (!done) { value = fn(); done = true; }
+    }
     py::object result() { compute(); return value; }
     py::object solver;
 private:
     std::function<py::object()> fn;
     py::object value;
+    std::mutex mutex;
     bool done = false;
 };
 

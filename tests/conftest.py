@@ -13,6 +13,31 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _cuda_devices():
+    """Number of CUDA devices seen through the C ABI (0 when the library or the driver is missing)"""
+    try:
+        import ctypes
+        from pybinding_b200 import _lib
+        count = ctypes.c_int(0)
+        if _lib.load().pbk_device_count(ctypes.byref(count)) != 0:
+            return 0
+        return count.value
+    except Exception:
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests are skipped (not failed) on a box without a CUDA device"""
+    if not any("gpu" in item.keywords for item in items):
+        return
+    if _cuda_devices() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (run on the B200 box: pytest -m gpu)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden():
     """The reference's own KPM baselines (tests/golden/make_golden.py)"""

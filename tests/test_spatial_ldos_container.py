@@ -31,3 +31,33 @@ def test_spatial_ldos_container():
     b = sel.find_nearest(pos, "B")
     start, end = system.sublattice_range("B")
     assert start <= sel.indices[b] < end
+
+
+def test_sublattice_range_without_the_method():
+    """A real pybinding System has no `sublattice_range` in Python (cppmodule/src/system.cpp:84-94): the range is read
+    off `system.sublattices`, an id array that compares with sublattice names (pybinding.support.alias.AliasArray)."""
+    from pybinding_b200.chebyshev import sublattice_range
+
+    class AliasIds(np.ndarray):
+        names = {"A": 0, "B": 1}
+
+        def __eq__(self, other):
+            return np.asarray(self).__eq__(self.names[other] if isinstance(other, str) else other)
+
+    class DuckSystem:   # the attributes chebyshev.py uses, nothing else
+        def __init__(self, reference):
+            self.positions = reference.positions
+            self.num_sites = reference.num_sites
+            start_b = reference.sublattice_range("B")[0]
+            ids = np.zeros(self.num_sites, np.int8)
+            ids[start_b:] = 1
+            self.sublattices = ids.view(AliasIds)
+
+    model = pb.graphene_rectangle(4.0, dtype=np.float32)
+    duck = DuckSystem(model.system)
+    assert not hasattr(duck, "sublattice_range")
+    for name in ("", "A", "B"):
+        assert sublattice_range(duck, name) == tuple(model.system.sublattice_range(name))
+    sel = SiteSelection(duck, np.arange(duck.num_sites))
+    b = sel.find_nearest([0.3, -0.4], "B")
+    assert model.system.sublattice_range("B")[0] <= b
