@@ -101,7 +101,6 @@ typedef struct pbk_stats {
     double moments_device_ms; /* device time of the whole moments phase (CUDA events on the library stream, from the
                                  first starter kernel to the moment copy-out, allreduce included) */
     int64_t bulk_launches;    /* step launches that ran the bulk-copy (TMA) staged kernel variant */
-    int64_t pair_launches;    /* launches of the two-step kernel (each advances the recursion by two steps = four moments) */
     int64_t graph_launches;   /* recursions replayed as one CUDA graph (small, launch-bound systems); their kernels are
                                  still counted in kernel_launches / step_launches */
 } pbk_stats;

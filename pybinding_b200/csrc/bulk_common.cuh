@@ -1,5 +1,5 @@
 // bulk_common.cuh -- mbarrier / bulk-copy (TMA engine) primitives and explicit shared-space loads shared by the
-// staged step kernels (kernels_bulk.cu, kernels_pair.cu).
+// staged step kernels (kernels_bulk.cu).
 #pragma once
 #include "step_common.cuh"
 

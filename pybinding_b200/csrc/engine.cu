@@ -59,6 +59,25 @@ void PinnedBuf::release() {
     if (ptr) { cudaFreeHost(ptr); ptr = nullptr; size = 0; }
 }
 
+template<class T> void RawVec<T>::release() {
+    if (p) { if (pinned_) cudaFreeHost(p); else delete[] p; }
+    p = nullptr; n = cap = 0; pinned_ = false;
+}
+template<class T> void RawVec<T>::resize_uninit(size_t count, bool pinned) {
+    if (count <= cap && (pinned_ || !pinned)) { n = count; return; }
+    release();
+    if (count == 0) return;
+    if (pinned) {
+        void* q = nullptr;
+        if (cudaMallocHost(&q, count * sizeof(T)) == cudaSuccess) { p = static_cast<T*>(q); pinned_ = true; }
+        else cudaGetLastError();
+    }
+    if (!p) p = new T[count];
+    n = cap = count;
+}
+template class RawVec<int32_t>;
+template class RawVec<char>;
+
 static double now_seconds() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -207,17 +226,16 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     bulk_xstage = env_int("PBK_XS", 1) != 0;
     identity_order = env_int("PBK_IDENTITY_ORDER", 0) != 0;
     coarse_sites = env_int("PBK_COARSE", 16);
+    dev_build = static_cast<int>(env_int("PBK_DEVBUILD", 1));
+    bcast_order = static_cast<int>(env_int("PBK_BCAST_ORDER", 1));
     macro_tiles = env_int("PBK_MACRO", 256);   // 65 k-site macro-blocks: +4 % on configs[1] in short runs, +1.5 % in the power-capped bench (profiles/r01_ab_order_v6.log)
     cone_mode = static_cast<int>(env_int("PBK_CONE", 1));
     graph_mode = static_cast<int>(env_int("PBK_GRAPH", 1));
     graph_max_bytes = 1e6 * static_cast<double>(env_int("PBK_GRAPH_MAX_MB", 64));
-    pair_mode = static_cast<int>(env_int("PBK_PAIR", 0));
-    pair_stages = static_cast<int>(env_int("PBK_PAIR_STAGES", 4));
-    pair_minb = static_cast<int>(env_int("PBK_PAIR_MINB", 0));
-    pair_max_r = static_cast<int>(env_int("PBK_PAIR_R", 0));
     PBK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (cudaEvent_t* e : {&ev0, &ev1, &ev2, &ev3, &ev_begin, &ev_end}) PBK_CUDA(cudaEventCreate(e));
     counter.alloc(64);
+    width_dev.alloc(64);
     PBK_CUDA(cudaMemsetAsync(counter.as(), 0, 64, stream));
     PBK_CUDA(cudaStreamSynchronize(stream));
     mt_state.alloc(sizeof(uint32_t) * (MT_N + 8));
@@ -244,41 +262,68 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
     if (dt < 0 || dt > 3) throw Error(PBK_INVALID_ARGUMENT, "invalid dtype");
     if (n_ <= 0 || !indptr || !indices || !data) throw Error(PBK_INVALID_ARGUMENT, "invalid Hamiltonian arrays");
     PBK_CUDA(cudaSetDevice(device));
-    dtype = dt;
-    n = n_;
-    int64_t const nnz = indptr[n];
-    double const t_set0 = now_seconds();
-    // the locality ordering of the full-system layout only needs the sparsity pattern: it runs on the caller's arrays in
-    // a second thread while this one copies them (parallel first touch)
-    cluster_queue.clear(); cluster_rmap.clear(); cluster_tile = 0;
-    std::unique_ptr<ScopedThread> ordering;   // joined on every exit path, exceptions of its body re-thrown after the join
-    if (locality_tile > 0 && !identity_order) {
-        cluster_tile = locality_tile;
-        ordering = std::make_unique<ScopedThread>([this, n_, indptr, indices] { cluster_order(n_, indptr, indices, cluster_tile, cluster_queue, cluster_rmap, macro_tiles, coarse_sites); });
+    bool const timing = std::getenv("PBK_TIMING") != nullptr;
+    // the order maps of the previous full-system layout are the scratch arrays of the next ordering (no allocation,
+    // no first-touch page faults when a context sees one Hamiltonian after another)
+    if (natural.host_order && natural.order_queue.size() >= cluster_queue.size()) {
+        cluster_queue.swap(natural.order_queue);
+        cluster_rmap.swap(natural.reorder_map);
     }
-    h_indptr.resize_uninit(static_cast<size_t>(n) + 1);
-    h_indices.resize_uninit(static_cast<size_t>(nnz));
-    h_data.resize_uninit(static_cast<size_t>(nnz) * dtype_size(dt));
-    parallel_rows(n + 1, [&](int64_t b, int64_t e) { std::memcpy(h_indptr.data() + b, indptr + b, sizeof(int32_t) * static_cast<size_t>(e - b)); });
-    parallel_rows(nnz, [&](int64_t b, int64_t e) {
-        std::memcpy(h_indices.data() + b, indices + b, sizeof(int32_t) * static_cast<size_t>(e - b));
-        size_t const sz = dtype_size(dt);
-        std::memcpy(h_data.data() + b * sz, static_cast<const char*>(data) + b * sz, sz * static_cast<size_t>(e - b));
-    });
-    double const t_copy = now_seconds();
-    if (ordering) ordering->join_and_rethrow();
-    if (std::getenv("PBK_TIMING")) std::fprintf(stderr, "[pbkpm] set_hamiltonian: copy %.3f s, + wait for the ordering %.3f s\n", t_copy - t_set0, now_seconds() - t_copy);
-    has_h = true;
+    has_h = false;
     clear_graphs();
     natural = DeviceHamiltonian();
     bfs_ready = BfsOrder();
     optimized = DeviceHamiltonian();
     unscaled = DeviceHamiltonian();
+    dtype = dt;
+    n = n_;
+    int64_t const nnz = indptr[n];
+    double const t_set0 = now_seconds();
+    // The locality ordering of the full-system layout only needs the sparsity pattern: it runs on the caller's arrays in
+    // a second thread while this one mirrors them into page-locked memory and uploads them.  With a communicator
+    // attached the Hamiltonian is the same on every rank (the sharding contract), so rank 0 alone computes the
+    // ordering and the others receive it by one broadcast over NVLink: set_hamiltonian is then a collective call.
+    cluster_tile = 0; cluster_on_device = false; cluster_on_host = false;
+    bool const want_order = locality_tile > 0 && !identity_order;
+    bool const receive_order = want_order && world > 1 && comm && bcast_order && nccl && nccl->Broadcast;
+    std::unique_ptr<ScopedThread> ordering;   // joined on every exit path, exceptions of its body re-thrown after the join
+    if (want_order && !(receive_order && rank != 0)) {
+        cluster_tile = locality_tile;
+        ordering = std::make_unique<ScopedThread>([this, n_, indptr, indices] { cluster_order(n_, indptr, indices, cluster_tile, cluster_queue, cluster_rmap, macro_tiles, coarse_sites); });
+    }
+    size_t const sz = dtype_size(dt);
+    h_indptr.resize_uninit(static_cast<size_t>(n) + 1, true);
+    h_indices.resize_uninit(static_cast<size_t>(nnz), true);
+    h_data.resize_uninit(static_cast<size_t>(nnz) * sz, true);
+    d_indptr.ensure(sizeof(int32_t) * (static_cast<size_t>(n) + 1));
+    d_indices.ensure(sizeof(int32_t) * static_cast<size_t>(std::max<int64_t>(nnz, 1)));
+    d_data.ensure(sz * static_cast<size_t>(std::max<int64_t>(nnz, 1)));
+    parallel_rows(n + 1, [&](int64_t b, int64_t e) { std::memcpy(h_indptr.data() + b, indptr + b, sizeof(int32_t) * static_cast<size_t>(e - b)); });
+    PBK_CUDA(cudaMemcpyAsync(d_indptr.as(), h_indptr.data(), sizeof(int32_t) * (static_cast<size_t>(n) + 1), cudaMemcpyHostToDevice, stream));
+    parallel_rows(nnz, [&](int64_t b, int64_t e) { std::memcpy(h_indices.data() + b, indices + b, sizeof(int32_t) * static_cast<size_t>(e - b)); });
+    PBK_CUDA(cudaMemcpyAsync(d_indices.as(), h_indices.data(), sizeof(int32_t) * static_cast<size_t>(nnz), cudaMemcpyHostToDevice, stream));
+    parallel_rows(nnz, [&](int64_t b, int64_t e) { std::memcpy(h_data.data() + b * sz, static_cast<const char*>(data) + b * sz, sz * static_cast<size_t>(e - b)); });
+    PBK_CUDA(cudaMemcpyAsync(d_data.as(), h_data.data(), sz * static_cast<size_t>(nnz), cudaMemcpyHostToDevice, stream));
+    dev_csr = true;
+    double const t_copy = now_seconds();
+    if (ordering) { ordering->join_and_rethrow(); cluster_on_host = true; }
+    double const t_order = now_seconds();
+    if (want_order && dev_build) {   // the ordering on the device: uploaded by its owner, broadcast to the other ranks
+        cluster_queue_dev.ensure(sizeof(int32_t) * static_cast<size_t>(n));
+        if (cluster_on_host) PBK_CUDA(cudaMemcpyAsync(cluster_queue_dev.as(), cluster_queue.data(), sizeof(int32_t) * static_cast<size_t>(n), cudaMemcpyHostToDevice, stream));
+        if (receive_order) { broadcast(cluster_queue_dev.as(), n, 0); cluster_tile = locality_tile; }
+        cluster_on_device = true;
+    }
+    PBK_CUDA(cudaStreamSynchronize(stream));
+    stats = pbk_stats{};
+    stats.h2d_bytes = static_cast<int64_t>(sizeof(int32_t) * (static_cast<size_t>(n) + 1 + nnz) + sz * nnz + (cluster_on_device && cluster_on_host ? sizeof(int32_t) * n : 0));
+    if (timing) std::fprintf(stderr, "[pbkpm] set_hamiltonian: mirror + upload issued %.3f s, + wait for the ordering %.3f s, + order upload / broadcast + sync %.3f s\n",
+                             t_copy - t_set0, t_order - t_copy, now_seconds() - t_order);
+    has_h = true;
     cone_gmap_rows = 0;
     have_bounds = false;
     lanczos_loops = 0;
     bounds_seconds = 0;
-    stats = pbk_stats{};
     if (config.min_energy != config.max_energy) {
         bounds_min = config.min_energy; bounds_max = config.max_energy;
         have_bounds = true;
@@ -576,8 +621,9 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
 
     mark("level-1 expansion");
     // ---- level 2: clusters inside every block, grown on the real graph; blocks are independent ----
-    queue.assign(n, 0);
-    rmap.assign(n, -1);
+    if (static_cast<int64_t>(queue.size()) != n) queue.assign(n, 0);   // every entry is written below
+    if (static_cast<int64_t>(rmap.size()) != n) rmap.resize(n);
+    parallel_rows(n, [&](int64_t b, int64_t e) { std::fill(rmap.begin() + b, rmap.begin() + e, -1); });
     mark("output arrays");
     int64_t const nblocks = static_cast<int64_t>(bstart.size()) - 1;
     auto order_block = [&](int64_t m) {
@@ -654,62 +700,56 @@ BfsOrder Engine::bfs_order(Indices const& target) const {
     return b;
 }
 
-/// Two-step kernel metadata (kernels_pair.cu): for every tile of `locality_tile` consecutive rows the sorted list of
-/// rows outside the tile that its rows reference (the one-ring halo), and the phase-2 column codes
-/// (>= 0: a row of the tile itself, < 0: -(1 + position in the halo list)), packed with the values like the ELL records.
-void Engine::build_pair_metadata(DeviceHamiltonian& dh, const int32_t* col, int64_t pitch, int k) {
-    int64_t const tile = dh.tile;
-    int64_t const ntiles = (n + tile - 1) / tile;
-    std::vector<int32_t> hptr(ntiles + 1, 0);
-    auto halo_of = [&](int64_t t, std::vector<int32_t>& buf) {
-        int64_t const r0 = t * tile, r1 = std::min<int64_t>(n, r0 + tile);
-        buf.clear();
-        for (int sidx = 0; sidx < k; ++sidx) {
-            const int32_t* cs = col + sidx * pitch;
-            for (int64_t r = r0; r < r1; ++r) { int32_t const c = cs[r]; if (c < r0 || c >= r1) buf.push_back(c); }
-        }
-        std::sort(buf.begin(), buf.end());
-        buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
-    };
-    parallel_rows(ntiles, [&](int64_t b, int64_t e) {
-        std::vector<int32_t> buf;
-        for (int64_t t = b; t < e; ++t) { halo_of(t, buf); hptr[t + 1] = static_cast<int32_t>(buf.size()); }
-    });
-    int hmax = 0;
-    for (int64_t t = 0; t < ntiles; ++t) { hmax = std::max(hmax, hptr[t + 1]); hptr[t + 1] += hptr[t]; }
-    std::vector<int32_t> hrows(std::max<int64_t>(hptr[ntiles], 1));
-    std::vector<int32_t> code(static_cast<size_t>(k) * pitch, 0);
-    parallel_rows(ntiles, [&](int64_t b, int64_t e) {
-        std::vector<int32_t> buf;
-        for (int64_t t = b; t < e; ++t) {
-            halo_of(t, buf);
-            std::copy(buf.begin(), buf.end(), hrows.begin() + hptr[t]);
-            int64_t const r0 = t * tile, r1 = std::min<int64_t>(n, r0 + tile);
-            for (int sidx = 0; sidx < k; ++sidx) {
-                const int32_t* cs = col + sidx * pitch;
-                int32_t* out = code.data() + sidx * pitch;
-                for (int64_t r = r0; r < r1; ++r) {
-                    int32_t const c = cs[r];
-                    if (c >= r0 && c < r1) { out[r] = c; }
-                    else { out[r] = -1 - static_cast<int32_t>(std::lower_bound(buf.begin(), buf.end(), c) - buf.begin()); }
-                }
-            }
-        }
-    });
-    dh.halo_max = hmax;
-    dh.halo_frac = static_cast<double>(hptr[ntiles]) / static_cast<double>(n);
-    dh.halo_ptr.alloc(sizeof(int32_t) * hptr.size());
-    dh.halo_rows.alloc(sizeof(int32_t) * hrows.size());
-    DevBuf code_dev(sizeof(int32_t) * code.size());
-    PBK_CUDA(cudaMemcpyAsync(dh.halo_ptr.as(), hptr.data(), sizeof(int32_t) * hptr.size(), cudaMemcpyHostToDevice, stream));
-    PBK_CUDA(cudaMemcpyAsync(dh.halo_rows.as(), hrows.data(), sizeof(int32_t) * hrows.size(), cudaMemcpyHostToDevice, stream));
-    PBK_CUDA(cudaMemcpyAsync(code_dev.as(), code.data(), sizeof(int32_t) * code.size(), cudaMemcpyHostToDevice, stream));
-    stats.h2d_bytes += static_cast<int64_t>(sizeof(int32_t) * (hptr.size() + hrows.size() + code.size()));
-    EllDev coded = dh.ell;
-    coded.col = code_dev.as<int32_t>();
-    dh.packed2.alloc(packed_ell_bytes(dtype, coded));
-    PBK_CUDA(launch_pack_ell(dtype, coded, dh.packed2.as(), stream));
+/// Rows of `dh` (order maps already on the device in dh.queue_dev / dh.perm, or none) from the resident CSR by one
+/// kernel (build.cu): mode = BUILD_SCALED (H~), BUILD_PLAIN (Lanczos) or BUILD_VELOCITY (operator of Kubo-Bastin).
+bool Engine::build_layout_on_device(DeviceHamiltonian& dh, int mode, Scale s, const float* positions_dev) {
+    if (!dev_build || !dev_csr) return false;
+    using R32 = float;
+    bool const single = dtype == F32 || dtype == C64;
+    // the scalar map in the Hamiltonian's real type, like build_ell_host: f = 2 / a, sb = b
+    double f = 1.0, sb = 0.0;
+    if (mode == BUILD_SCALED) {
+        if (single) { R32 const sa = static_cast<R32>(s.a); f = static_cast<double>(R32{2} / sa); sb = static_cast<double>(static_cast<R32>(s.b)); }
+        else { f = 2.0 / s.a; sb = s.b; }
+    }
+    PBK_CUDA(launch_row_width(d_indptr.as<int32_t>(), d_indices.as<int32_t>(), n, mode == BUILD_SCALED && sb != 0.0, width_dev.as<int>(), stream));
+    int width = 0;
+    PBK_CUDA(cudaMemcpyAsync(&width, width_dev.as(), sizeof(int), cudaMemcpyDeviceToHost, stream));
     PBK_CUDA(cudaStreamSynchronize(stream));
+    int const k = std::max(width, 1);
+    if (k > build_max_width()) return false;
+    int64_t const pitch = (n + 31) / 32 * 32;
+    dh.val.alloc(static_cast<size_t>(k) * pitch * dtype_size(dtype));
+    dh.col.alloc(static_cast<size_t>(k) * pitch * sizeof(int32_t));
+    BuildArgs a;
+    a.indptr = d_indptr.as<int32_t>(); a.indices = d_indices.as<int32_t>(); a.n = n;
+    a.queue = dh.reordered ? dh.queue_dev.as<int32_t>() : nullptr;
+    a.perm = dh.reordered ? dh.perm.as<int32_t>() : nullptr;
+    a.mode = mode; a.f = f; a.sb = sb; a.positions = positions_dev;
+    a.k = k; a.pitch = pitch; a.col = dh.col.as<int32_t>();
+    PBK_CUDA(launch_csr_to_ell(dtype, a, d_data.as(), dh.val.as(), stream));
+    launches += 2;
+    dh.ell = EllDev{dh.val.as(), dh.col.as<int32_t>(), n, pitch, k};
+    return true;
+}
+
+/// host copies of a layout's order maps: they exist already when the host computed the order, and are downloaded on
+/// first use when the order arrived by broadcast (only index look-ups and host-built operators need them)
+void Engine::ensure_host_order(DeviceHamiltonian& dh) {
+    if (!dh.reordered || dh.host_order) return;
+    PBK_CUDA(cudaSetDevice(device));
+    dh.reorder_map.resize(static_cast<size_t>(n));
+    dh.order_queue.resize(static_cast<size_t>(n));
+    PBK_CUDA(cudaMemcpyAsync(dh.reorder_map.data(), dh.perm.as(), sizeof(int32_t) * static_cast<size_t>(n), cudaMemcpyDeviceToHost, stream));
+    PBK_CUDA(cudaMemcpyAsync(dh.order_queue.data(), dh.queue_dev.as(), sizeof(int32_t) * static_cast<size_t>(n), cudaMemcpyDeviceToHost, stream));
+    PBK_CUDA(cudaStreamSynchronize(stream));
+    stats.d2h_bytes += static_cast<int64_t>(2 * sizeof(int32_t) * n);
+    dh.host_order = true;
+}
+
+void Engine::broadcast(void* dev, int64_t count_int32, int root) {
+    if (world <= 1 || !comm) return;
+    nccl->check(nccl->Broadcast(dev, dev, static_cast<size_t>(count_int32), /*ncclInt32*/ 2, root, comm, stream), "ncclBroadcast");
 }
 
 void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int order, Indices const& target) {
@@ -728,21 +768,24 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
         std::fprintf(stderr, "[pbkpm] build_device_hamiltonian: %-28s %.3f s\n", what, t - t_mark);
         t_mark = t;
     };
+    // ---- row order: host vectors (queue: new -> old, dh.reorder_map: old -> new) and / or the device copy ----
     std::vector<int32_t> queue;
+    bool order_on_device = false;
     if (order == ORDER_CLUSTER) {
         if (identity_order) {   // PBK_IDENTITY_ORDER=1: the caller's site order, cut into tiles of consecutive rows (staged kernel applies)
             queue.resize(n);
             for (int64_t i = 0; i < n; ++i) queue[i] = static_cast<int32_t>(i);
             dh.reorder_map = queue;
-        } else if (cluster_tile == locality_tile && static_cast<int64_t>(cluster_queue.size()) == n) {   // computed by set_hamiltonian
-            queue = std::move(cluster_queue);
-            dh.reorder_map = std::move(cluster_rmap);
-            cluster_queue.clear(); cluster_rmap.clear(); cluster_tile = 0;
+        } else if (cluster_tile == locality_tile && (cluster_on_host || cluster_on_device)) {   // computed / received by set_hamiltonian
+            if (cluster_on_host) { queue.swap(cluster_queue); dh.reorder_map.swap(cluster_rmap); }
+            else dh.host_order = false;
+            if (cluster_on_device) { dh.queue_dev = std::move(cluster_queue_dev); order_on_device = true; }
+            cluster_tile = 0; cluster_on_host = cluster_on_device = false;
         } else {
             cluster_order(n, h_indptr.data(), h_indices.data(), locality_tile, queue, dh.reorder_map, macro_tiles, coarse_sites);
         }
-        for (int32_t i : target.src) dh.idx.src.push_back(dh.reorder_map[i]);
-        for (int32_t i : target.dest) dh.idx.dest.push_back(dh.reorder_map[i]);
+        dh.idx = target;   // positions in this layout are looked up where they are needed (ensure_host_order)
+        if (dh.host_order) { dh.idx = Indices{}; for (int32_t i : target.src) dh.idx.src.push_back(dh.reorder_map[i]); for (int32_t i : target.dest) dh.idx.dest.push_back(dh.reorder_map[i]); }
         dh.map.data = {static_cast<int32_t>(n)};
         dh.reordered = true;
         dh.tile = locality_tile;
@@ -766,45 +809,61 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
         dh.idx = target;
         dh.map.data = {static_cast<int32_t>(n)};
     }
-
-    HostEll ell;
-    const int32_t* q = reorder ? queue.data() : nullptr;
-    const int32_t* rm = reorder ? dh.reorder_map.data() : nullptr;
     mark("row order");
-    if (order == ORDER_CLUSTER) dh.order_queue = queue;  // operators of the same calculation are laid out alike
-    // the full-system layout (the big, long-lived one) is staged in the context's page-locked buffers
-    PinnedBuf* const sv = (&dh == &natural) ? &stage_val : nullptr;
-    PinnedBuf* const sc = (&dh == &natural) ? &stage_col : nullptr;
-    switch (dtype) {
-        case F32: ell = build_ell_host<float>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const float*>(h_data.data()), scaled, s, q, rm, sv, sc); break;
-        case C64: ell = build_ell_host<cf>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cf*>(h_data.data()), scaled, s, q, rm, sv, sc); break;
-        case F64: ell = build_ell_host<double>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const double*>(h_data.data()), scaled, s, q, rm, sv, sc); break;
-        default: ell = build_ell_host<cd>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cd*>(h_data.data()), scaled, s, q, rm, sv, sc); break;
+
+    // ---- device path: the rows are written by a kernel from the resident CSR ----
+    bool built = false;
+    if (dev_build && dev_csr) {
+        if (reorder) {
+            if (!order_on_device) {
+                dh.queue_dev.alloc(sizeof(int32_t) * static_cast<size_t>(n));
+                PBK_CUDA(cudaMemcpyAsync(dh.queue_dev.as(), queue.data(), sizeof(int32_t) * static_cast<size_t>(n), cudaMemcpyHostToDevice, stream));
+                stats.h2d_bytes += static_cast<int64_t>(sizeof(int32_t) * n);
+            }
+            dh.perm.alloc(sizeof(int32_t) * static_cast<size_t>(n));
+            PBK_CUDA(launch_invert_order(dh.queue_dev.as<int32_t>(), n, dh.perm.as<int32_t>(), stream));
+            ++launches;
+        }
+        built = build_layout_on_device(dh, scaled ? BUILD_SCALED : BUILD_PLAIN, s, nullptr);
+        if (built) mark("rows built on the device");
     }
-    mark("scaled ELL on the host");
-    dh.val.alloc(ell.val_bytes);
-    dh.col.alloc(ell.col_count * sizeof(int32_t));
-    mark("device allocation");
-    PBK_CUDA(cudaMemcpyAsync(dh.val.as(), ell.val, ell.val_bytes, cudaMemcpyHostToDevice, stream));
-    PBK_CUDA(cudaMemcpyAsync(dh.col.as(), ell.col, ell.col_count * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-    stats.h2d_bytes += static_cast<int64_t>(ell.val_bytes + ell.col_count * sizeof(int32_t));
-    if (reorder) {
-        dh.perm.alloc(sizeof(int32_t) * n);
-        PBK_CUDA(cudaMemcpyAsync(dh.perm.as(), dh.reorder_map.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream));
-        stats.h2d_bytes += static_cast<int64_t>(sizeof(int32_t) * n);
+    if (!built) {   // host path: scaled ELL written by the host threads into page-locked staging, one upload
+        if (reorder && !dh.host_order) ensure_host_order(dh);
+        if (reorder && queue.empty()) queue = dh.order_queue;
+        HostEll ell;
+        const int32_t* q = reorder ? queue.data() : nullptr;
+        const int32_t* rm = reorder ? dh.reorder_map.data() : nullptr;
+        // the full-system layout (the big, long-lived one) is staged in the context's page-locked buffers
+        PinnedBuf* const sv = (&dh == &natural) ? &stage_val : nullptr;
+        PinnedBuf* const sc = (&dh == &natural) ? &stage_col : nullptr;
+        switch (dtype) {
+            case F32: ell = build_ell_host<float>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const float*>(h_data.data()), scaled, s, q, rm, sv, sc); break;
+            case C64: ell = build_ell_host<cf>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cf*>(h_data.data()), scaled, s, q, rm, sv, sc); break;
+            case F64: ell = build_ell_host<double>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const double*>(h_data.data()), scaled, s, q, rm, sv, sc); break;
+            default: ell = build_ell_host<cd>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cd*>(h_data.data()), scaled, s, q, rm, sv, sc); break;
+        }
+        mark("scaled ELL on the host");
+        dh.val.alloc(ell.val_bytes);
+        dh.col.alloc(ell.col_count * sizeof(int32_t));
+        PBK_CUDA(cudaMemcpyAsync(dh.val.as(), ell.val, ell.val_bytes, cudaMemcpyHostToDevice, stream));
+        PBK_CUDA(cudaMemcpyAsync(dh.col.as(), ell.col, ell.col_count * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+        stats.h2d_bytes += static_cast<int64_t>(ell.val_bytes + ell.col_count * sizeof(int32_t));
+        if (reorder) {
+            if (!dh.perm.bytes()) dh.perm.alloc(sizeof(int32_t) * static_cast<size_t>(n));
+            PBK_CUDA(cudaMemcpyAsync(dh.perm.as(), dh.reorder_map.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream));
+            stats.h2d_bytes += static_cast<int64_t>(sizeof(int32_t) * n);
+        }
+        dh.ell = EllDev{dh.val.as(), dh.col.as<int32_t>(), n, ell.pitch, ell.k};
+        PBK_CUDA(cudaStreamSynchronize(stream));   // `ell` may live in pageable memory that goes out of scope here
     }
-    dh.ell.val = dh.val.as();
-    dh.ell.col = dh.col.as<int32_t>();
-    dh.ell.rows = n;
-    dh.ell.pitch = ell.pitch;
-    dh.ell.k = ell.k;
-    if (order == ORDER_CLUSTER && bulk_stages >= 2) {  // row-major records for the bulk-copy staged step kernel
+    if (order == ORDER_CLUSTER) dh.order_queue = std::move(queue);  // operators of the same calculation are laid out alike
+    if (order == ORDER_CLUSTER && bulk_stages >= 2) {  // granule-packed records for the bulk-copy staged step kernel
         dh.packed.alloc(packed_ell_bytes(dtype, dh.ell));
         PBK_CUDA(launch_pack_ell(dtype, dh.ell, dh.packed.as(), stream));
-        if (pair_mode) build_pair_metadata(dh, ell.col, ell.pitch, ell.k);
+        ++launches;
     }
     PBK_CUDA(cudaStreamSynchronize(stream));
-    mark("upload + pack");
+    mark("upload / pack");
     dh.original_idx = target;
     dh.valid = true;
     dh.seconds = now_seconds() - t0;
@@ -818,6 +877,7 @@ DeviceHamiltonian& Engine::natural_hamiltonian() {
 DeviceHamiltonian& Engine::optimized_for(Indices const& target) {
     if (!config.optimal_size) {  // no light-cone slicing requested: the natural order serves every index
         auto& h = natural_hamiltonian();
+        ensure_host_order(h);
         h.idx = Indices{};
         for (int32_t i : target.src) h.idx.src.push_back(h.reordered ? h.reorder_map[i] : i);
         for (int32_t i : target.dest) h.idx.dest.push_back(h.reordered ? h.reorder_map[i] : i);
@@ -835,8 +895,30 @@ DeviceHamiltonian& Engine::unscaled_hamiltonian() {
     return unscaled;
 }
 
-/// velocity operator V_ij = H_ij * (pos_i - pos_j) on the unscaled H (src/kpm/Moments.cpp:132-156)
-void Engine::upload_operator(DeviceHamiltonian& dh, const float* pos, DeviceHamiltonian const& like) {
+/// velocity operator V_ij = H_ij * (pos_i - pos_j) on the unscaled H (src/kpm/Moments.cpp:132-156), laid out like `like`
+void Engine::upload_operator(DeviceHamiltonian& dh, const float* pos, DeviceHamiltonian& like) {
+    dh = DeviceHamiltonian();
+    dh.tile = like.tile;
+    dh.map.data = {static_cast<int32_t>(n)};
+    if (dev_build && dev_csr && (!like.reordered || (like.queue_dev.bytes() && like.perm.bytes()))) {
+        // on the device from the resident CSR: only the coordinates go up
+        DevBuf pos_dev(sizeof(float) * static_cast<size_t>(n));
+        PBK_CUDA(cudaMemcpyAsync(pos_dev.as(), pos, sizeof(float) * static_cast<size_t>(n), cudaMemcpyHostToDevice, stream));
+        stats.h2d_bytes += static_cast<int64_t>(sizeof(float) * n);
+        dh.reordered = like.reordered;
+        if (like.reordered) {   // borrow the order maps of the layout (device-to-device copies: the operator is short-lived)
+            dh.queue_dev.alloc(like.queue_dev.bytes());
+            dh.perm.alloc(like.perm.bytes());
+            PBK_CUDA(cudaMemcpyAsync(dh.queue_dev.as(), like.queue_dev.as(), sizeof(int32_t) * static_cast<size_t>(n), cudaMemcpyDeviceToDevice, stream));
+            PBK_CUDA(cudaMemcpyAsync(dh.perm.as(), like.perm.as(), sizeof(int32_t) * static_cast<size_t>(n), cudaMemcpyDeviceToDevice, stream));
+        }
+        bool const ok = build_layout_on_device(dh, BUILD_VELOCITY, Scale(), pos_dev.as<float>());
+        PBK_CUDA(cudaStreamSynchronize(stream));
+        dh.reordered = false;   // as before: the operator itself carries no order maps, it is only laid out like `like`
+        dh.queue_dev = DevBuf(); dh.perm = DevBuf();
+        if (ok) { dh.valid = true; return; }
+    }
+    ensure_host_order(like);
     int64_t const nnz = h_indptr[n];
     std::vector<char> data(static_cast<size_t>(nnz) * dtype_size(dtype));
     auto fill = [&](auto* out, auto const* in) {
@@ -862,8 +944,6 @@ void Engine::upload_operator(DeviceHamiltonian& dh, const float* pos, DeviceHami
         case F64: ell = build_ell_host<double>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const double*>(data.data()), false, Scale(), q, rm); break;
         default: ell = build_ell_host<cd>(n, h_indptr.data(), h_indices.data(), reinterpret_cast<const cd*>(data.data()), false, Scale(), q, rm); break;
     }
-    dh = DeviceHamiltonian();
-    dh.tile = like.tile;
     dh.val.alloc(ell.val_bytes);
     dh.col.alloc(ell.col_count * sizeof(int32_t));
     PBK_CUDA(cudaMemcpyAsync(dh.val.as(), ell.val, ell.val_bytes, cudaMemcpyHostToDevice, stream));
@@ -871,13 +951,13 @@ void Engine::upload_operator(DeviceHamiltonian& dh, const float* pos, DeviceHami
     PBK_CUDA(cudaStreamSynchronize(stream));   // `ell` (pageable host memory) goes out of scope with this function
     stats.h2d_bytes += static_cast<int64_t>(ell.val_bytes + ell.col_count * sizeof(int32_t));
     dh.ell = EllDev{dh.val.as(), dh.col.as<int32_t>(), n, ell.pitch, ell.k};
-    dh.map.data = {static_cast<int32_t>(n)};
     dh.valid = true;
 }
 
 /// generic operator of KPM.moments(op=...): c128 CSR cast to the Hamiltonian's scalar type (force_cast)
 void Engine::upload_csr_operator(DeviceHamiltonian& dh, int64_t rows, const int32_t* indptr, const int32_t* indices, const cd* data,
-                                 DeviceHamiltonian const& like) {
+                                 DeviceHamiltonian& like) {
+    ensure_host_order(like);
     int64_t const nnz = indptr[rows];
     HostEll ell;
     const int32_t* q = like.reordered ? like.order_queue.data() : nullptr;
@@ -1032,12 +1112,11 @@ int Engine::pick_batch(int vectors, int extra_blocks) const {
     cudaMemGetInfo(&free_b, &total_b);
     // vec_a / vec_b (+ extra) blocks and the raw random words of one lane
     double const per_lane = static_cast<double>(n) * (dtype_size(dtype) * (2 + extra_blocks) + 4 * dtype_words(dtype));
-    double const reusable = static_cast<double>(vec_a.bytes() + vec_b.bytes() + vec_c.bytes() + vec_d.bytes() + raw.bytes());
+    double const reusable = static_cast<double>(vec_a.bytes() + vec_b.bytes() + raw.bytes());
     int cap = static_cast<int>((0.85 * static_cast<double>(free_b) + reusable) / per_lane);
     int const hard = 4096 / dtype_size(dtype);  // 256 chunks of 16 bytes per row
     cap = std::min(cap, hard);
     cap = std::min(cap, config.max_batch > 0 ? config.max_batch : 64);
-    if (pair_mode && pair_max_r > 0) cap = std::min(cap, pair_max_r);
     if (cap < 1) throw Error(PBK_RUNTIME_ERROR, "pbkpm: not enough device memory for one KPM vector pair");
     // a pass of more than one vector is padded to whole 16-byte chunks (lane_pad), so the batch itself must be a
     // multiple of the chunk width: buffers are sized for `rb` lanes and every launch uses lane_pad(lanes) <= rb
@@ -1053,7 +1132,7 @@ void Engine::ensure_moment_buffers(int R, int M) {
     mom.ensure(sizeof(double) * 2 * static_cast<size_t>(R) * M + 64);
     m01.ensure(sizeof(double) * 3 * R + 64);
     acc.ensure(sizeof(double) * 2 * M + 64);
-    partials.ensure(sizeof(double) * 2 * 3 * static_cast<size_t>(R) * max_step_blocks(num_sms));  // x2: the two-step kernel reduces two steps
+    partials.ensure(sizeof(double) * 3 * static_cast<size_t>(R) * max_step_blocks(num_sms));
     scratch.ensure(sizeof(double) * 2 * num_sms * 8);
 }
 
@@ -1074,38 +1153,9 @@ void Engine::step(DeviceHamiltonian const& h, const void* x, void* y, void* y2, 
     stats.step_bytes += static_cast<double>(nrows) * (h.ell.k * (s + 4.0) + static_cast<double>(R) * s * (2 + (subtract ? 1 : 0) + (y2 ? 1 : 0)));
 }
 
-bool Engine::step_pair(DeviceHamiltonian const& h, const void* a, const void* b, void* c, void* d, int R, int M, int nstep) {
-    PairArgs p;
-    p.packed = h.packed.as(); p.packed2 = h.packed2.as(); p.halo_ptr = h.halo_ptr.as<int32_t>(); p.halo_rows = h.halo_rows.as<int32_t>();
-    p.halo_max = h.halo_max;
-    p.a = a; p.b = b; p.c = c; p.d = d;
-    p.nrows = n; p.tile = h.tile; p.R = R; p.k = h.ell.k;
-    p.partials = partials.as<double>(); p.counter = counter.as<unsigned>(); p.mom = mom.as<double>(); p.m01 = m01.as<double>();
-    p.M = M; p.n = nstep; p.stages = pair_stages; p.blocks_per_sm = step_blocks_per_sm; p.min_blocks = pair_minb;
-    bool handled = false;
-    LaunchInfo info;
-    PBK_CUDA(launch_step_pair(dtype, p, num_sms, stream, &info, &handled));
-    if (!handled) return false;
-    ++launches;
-    ++stats.step_launches;
-    ++stats.pair_launches;
-    int const s = dtype_size(dtype);
-    stats.step_bytes += 2.0 * static_cast<double>(n) * (h.ell.k * (s + 4.0) + 3.0 * R * s);  // the per-step model, twice
-    return true;
-}
-
 void Engine::run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_size) {
     void* r0 = vec_a.as();
     void* r1 = vec_b.as();
-    // two-step kernel: full-system locality layout with halo metadata, and a halo fraction that leaves a gain
-    bool pair = pair_mode && !opt_size && h.packed2.bytes() && (h.halo_frac < 0.6 || pair_mode >= 2) && M / 2 >= 3;  // PBK_PAIR=2: regardless of the halo share
-    void* r2 = nullptr; void* r3 = nullptr;
-    if (pair) {
-        size_t const block_bytes = static_cast<size_t>(n) * R * dtype_size(dtype);
-        vec_c.ensure(block_bytes);
-        vec_d.ensure(block_bytes);
-        r2 = vec_c.as(); r3 = vec_d.as();
-    }
     PBK_CUDA(cudaEventRecord(ev2, stream));
     int64_t const nv = h.vec_rows > 0 ? h.vec_rows : n;
     auto emit = [&]() {
@@ -1117,15 +1167,6 @@ void Engine::run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_siz
         }
         step(h, r0, r1, nullptr, init_rows, R, false, true, 0.5, M, 0, FIN_INIT);
         for (int k = 2; k <= M / 2; ++k) {  // calc_moments::basic (diagonal), calc_moments.hpp:36-51
-            if (pair && k + 1 <= M / 2) {   // r0 = r_{k-2}, r1 = r_{k-1}  ->  r2 = r_k, r3 = r_{k+1}
-                if (step_pair(h, r0, r1, r2, r3, R, M, k)) {
-                    std::swap(r0, r2);
-                    std::swap(r1, r3);
-                    ++k;
-                    continue;
-                }
-                pair = false;   // geometry not supported: single steps from here on
-            }
             int64_t const rows = opt_size ? h.map.optimal_size(k, M) : nv;
             step(h, r1, r0, nullptr, rows, R, true, true, 1.0, M, k, FIN_STEP);
             std::swap(r0, r1);
@@ -1133,7 +1174,7 @@ void Engine::run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_siz
     };
     // Small systems are launch-bound (a step is a few microseconds of work): capture the whole sequence once as a
     // CUDA graph and replay it on later runs with the same buffers and row counts.
-    bool const graphable = graph_mode && !pair && !h.transient && M / 2 >= 8 &&
+    bool const graphable = graph_mode && !h.transient && M / 2 >= 8 &&
                            static_cast<double>(nv) * R * dtype_size(dtype) <= graph_max_bytes;
     bool done = false;
     if (graphable) {
@@ -1339,7 +1380,7 @@ void Engine::moments_dos(int M, int num_random, cd* out) {
     ensure_moment_buffers(1, M);
     PBK_CUDA(cudaMemsetAsync(acc.as(), 0, sizeof(double) * 2 * M, stream));
     if (count > 0) {
-        int const rb = pick_batch(count, pair_mode ? 2 : 0);
+        int const rb = pick_batch(count, 0);
         ensure_moment_buffers(rb, M);
         size_t const block_bytes = static_cast<size_t>(n) * rb * dtype_size(dtype);
         vec_a.ensure(block_bytes);
@@ -1370,7 +1411,7 @@ void Engine::moments_diagonal(int M, const cd* r0, int count, cd* out) {
     auto& h = natural_hamiltonian();
     reset_stats(M, h, false, count);
     begin_moments();
-    int const rb = pick_batch(count, pair_mode ? 2 : 0);
+    int const rb = pick_batch(count, 0);
     ensure_moment_buffers(rb, M);
     size_t const block_bytes = static_cast<size_t>(n) * rb * dtype_size(dtype);
     vec_a.ensure(block_bytes);
@@ -1672,6 +1713,7 @@ void Engine::moments_ldos(int M, const int32_t* idx, int nidx, cd* out) {
     DeviceHamiltonian* hp = nullptr;
     if (spread) {
         auto& hn = natural_hamiltonian();
+        ensure_host_order(hn);
         hn.idx = Indices{};
         for (int32_t i : target.src) hn.idx.src.push_back(hn.reordered ? hn.reorder_map[i] : i);
         hn.idx.dest = hn.idx.src;
@@ -1689,7 +1731,7 @@ void Engine::moments_ldos(int M, const int32_t* idx, int nidx, cd* out) {
     shard(nidx, &first, &count);
     std::vector<cd> table(static_cast<size_t>(M) * nidx, cd(0, 0));
     if (count > 0) {
-        int const rb = pick_batch(count, pair_mode ? 2 : 0);
+        int const rb = pick_batch(count, 0);
         ensure_moment_buffers(rb, M);
         size_t const block_bytes = static_cast<size_t>(n) * rb * dtype_size(dtype);
         vec_a.ensure(block_bytes);

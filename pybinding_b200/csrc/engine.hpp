@@ -49,15 +49,29 @@ private:
 /// Host array without value-initialisation: large buffers are first touched by the (parallel) code that fills them
 template<class T> class RawVec {
 public:
-    void resize_uninit(size_t count) { if (count != n) { p.reset(count ? new T[count] : nullptr); n = count; } }
-    T* data() { return p.get(); }
-    const T* data() const { return p.get(); }
+    RawVec() = default;
+    RawVec(RawVec const&) = delete;
+    RawVec& operator=(RawVec const&) = delete;
+    RawVec(RawVec&& o) noexcept : p(o.p), n(o.n), cap(o.cap), pinned_(o.pinned_) { o.p = nullptr; o.n = o.cap = 0; o.pinned_ = false; }
+    RawVec& operator=(RawVec&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; pinned_ = o.pinned_; o.p = nullptr; o.n = o.cap = 0; o.pinned_ = false; }
+        return *this;
+    }
+    ~RawVec() { release(); }
+    /// `pinned`: page-locked storage (uploads at the link rate; pageable memory when the driver refuses).  The storage is
+    /// kept when it is large enough, so a context that sees several Hamiltonians pays for allocation and pinning once.
+    void resize_uninit(size_t count, bool pinned = false);
+    T* data() { return p; }
+    const T* data() const { return p; }
     size_t size() const { return n; }
+    bool is_pinned() const { return pinned_; }
     T& operator[](size_t i) { return p[i]; }
     T const& operator[](size_t i) const { return p[i]; }
 private:
-    std::unique_ptr<T[]> p;
-    size_t n = 0;
+    void release();
+    T* p = nullptr;
+    size_t n = 0, cap = 0;
+    bool pinned_ = false;
 };
 
 /// Page-locked host staging buffer, kept by the context and grown on demand: uploads run at the link rate and the
@@ -113,11 +127,9 @@ struct DeviceHamiltonian {
     SliceMap map;
     std::vector<int32_t> reorder_map;  // original -> device row (empty: identity)
     DevBuf val, col, perm;
+    DevBuf queue_dev;              // row of the layout -> original site, on the device (layouts built by build.cu)
+    bool host_order = true;        // reorder_map / order_queue hold the host copies of perm / queue_dev (else: downloaded on first use)
     DevBuf packed;                 // row-major packed copy of the ELL arrays for the bulk-copy staged step kernel (ORDER_CLUSTER only)
-    // two-step kernel (kernels_pair.cu): per-tile halo lists and the phase-2 records (column codes)
-    DevBuf packed2, halo_ptr, halo_rows;
-    int halo_max = 0;              // longest halo list (rows)
-    double halo_frac = 0;          // halo rows / rows: the redundant share of phase 1
     EllDev ell;
     double seconds = 0;
     uint64_t memory() const { return static_cast<uint64_t>(ell.rows) * ell.k * 0 + val.bytes() + col.bytes(); }
@@ -152,6 +164,7 @@ struct NcclApi {
     void* handle = nullptr;
     int (*GetUniqueId)(void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;   // optional
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 
@@ -163,6 +176,7 @@ struct NcclApi {
         if (!handle) throw Error(PBK_NCCL_ERROR, std::string("cannot load libnccl.so.2: ") + dlerror());
         GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(handle, "ncclGetUniqueId"));
         AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(handle, "ncclAllReduce"));
+        Broadcast = reinterpret_cast<decltype(Broadcast)>(dlsym(handle, "ncclBroadcast"));
         CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
         GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
         init_rank = dlsym(handle, "ncclCommInitRank");
@@ -222,8 +236,6 @@ private:
     int bulk_stages = 4;         // pipeline depth of the bulk-copy staged step kernel (0: general kernel only)
     bool bulk_xstage = true;     // staged kernel: the CTA's own x rows go through shared memory too
     int64_t locality_tile = 0;   // rows per locality cluster of the full-system layout (0: keep the caller's order)
-    int pair_mode = 0;           // two Chebyshev steps per launch (kernels_pair.cu) where the layout allows it
-    int pair_stages = 4, pair_minb = 0, pair_max_r = 0;
     pbk_config config{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_begin = nullptr, ev_end = nullptr;
@@ -233,13 +245,21 @@ private:
     // ---- host copy of the Hamiltonian (original order, unscaled) ----
     int dtype = -1;
     int64_t n = 0;
-    RawVec<int32_t> h_indptr, h_indices;
+    RawVec<int32_t> h_indptr, h_indices;   // page-locked mirror of the caller's arrays (host-side graph walks: BFS, light cones)
     RawVec<char> h_data;
     bool has_h = false;
-    // locality ordering of the full-system layout, computed while set_hamiltonian copies the arrays
+    DevBuf d_indptr, d_indices, d_data;    // the same CSR on the device: every layout is built from it by a kernel (build.cu)
+    bool dev_csr = false;
+    int dev_build = 1;                     // PBK_DEVBUILD=0: build the layouts on the host (the round-1 path; A/B and fallback)
+    int bcast_order = 1;                   // PBK_BCAST_ORDER=0: every rank computes the locality ordering itself
+    // locality ordering of the full-system layout, computed while set_hamiltonian copies the arrays (rank 0 only when a
+    // communicator is attached: the other ranks receive it over NVLink)
     std::vector<int32_t> cluster_queue, cluster_rmap;
     int64_t cluster_tile = 0;
-    PinnedBuf stage_val, stage_col;   // ELL staging of the full-system layout
+    DevBuf cluster_queue_dev;              // the ordering on the device (uploaded or received by broadcast)
+    bool cluster_on_device = false, cluster_on_host = false;
+    PinnedBuf stage_val, stage_col;   // ELL staging of the full-system layout (host build path)
+    DevBuf width_dev;                 // one int: widest row of the layout being built
 
     // ---- bounds ----
     bool have_bounds = false;
@@ -253,7 +273,6 @@ private:
     DeviceHamiltonian unscaled;   // original values, original order (Lanczos)
 
     // ---- work buffers ----
-    DevBuf vec_c, vec_d;         // second vector pair of the two-step kernel
     DevBuf cone_val, cone_col, cone_queue, cone_gmap, cone_table;   // light-cone sub-system of the site being processed
     int64_t cone_gmap_rows = 0;  // cone_gmap holds -1 for this many rows
     int64_t coarse_sites = 16;   // PBK_COARSE: consecutive sites per super-node of the macro-block pass (1: no coarsening)
@@ -287,24 +306,25 @@ private:
     BfsOrder bfs_order(Indices const& target) const;
     BfsOrder bfs_ready;           // relabelling computed ahead of build_device_hamiltonian (moments_ldos)
     void build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int order, Indices const& target);
+    /// the layout's rows written by build.cu from the resident CSR; false: not applicable (rows too long), use the host path
+    bool build_layout_on_device(DeviceHamiltonian& dh, int mode, Scale s, const float* positions_dev);
+    void ensure_host_order(DeviceHamiltonian& dh);   // host copies of a layout's order maps (downloaded on first use)
+    void broadcast(void* dev, int64_t count_int32, int root);
     DeviceHamiltonian& natural_hamiltonian();
     DeviceHamiltonian& optimized_for(Indices const& target);
     DeviceHamiltonian& unscaled_hamiltonian();
     Cone bfs_cone(int32_t src, int depth, std::vector<int32_t>& mark) const;
     /// LDOS moments on per-site light-cone sub-systems cut out of the resident Hamiltonian; false: the full-system batch is cheaper
     bool moments_ldos_cones(int M, Indices const& target, cd* out);
-    void upload_operator(DeviceHamiltonian& dh, const float* positions, DeviceHamiltonian const& like);  // velocity operator
+    void upload_operator(DeviceHamiltonian& dh, const float* positions, DeviceHamiltonian& like);  // velocity operator
     void upload_csr_operator(DeviceHamiltonian& dh, int64_t rows, const int32_t* indptr, const int32_t* indices, const cd* data,
-                             DeviceHamiltonian const& like);
+                             DeviceHamiltonian& like);
 
     int pick_batch(int vectors, int extra_blocks) const;
     int lane_pad(int R) const;
     void ensure_moment_buffers(int R, int M);
     void step(DeviceHamiltonian const& h, const void* x, void* y, void* y2, int64_t nrows, int R, bool subtract, bool sums,
               double scale, int M, int nstep, int fin);
-    /// two steps in one launch: c = H b - a, d = H c - b (moments of steps nstep and nstep + 1); false: not applicable
-    bool step_pair(DeviceHamiltonian const& h, const void* a, const void* b, void* c, void* d, int R, int M, int nstep);
-    void build_pair_metadata(DeviceHamiltonian& dh, const int32_t* col, int64_t pitch, int k);
     /// diagonal recursion for the R vectors in vec_a (r0); moments land in `mom` ([R][M] c128)
     void run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_size);
     /// off-diagonal recursion for the single vector in vec_a; `collect(n, r, half)` is called for every moment

@@ -58,37 +58,34 @@ struct LaunchInfo { int grid = 0, block = 0, V = 0, K = 0, bulk = 0; };
 cudaError_t launch_step(int dtype, StepArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info);
 /// Staged variant (kernels_bulk.cu): *handled == false means "not applicable, use the general kernel".
 cudaError_t launch_step_bulk(int dtype, StepArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info, bool* handled);
-/// Row-major packed copy of an ELL matrix for the staged variant: per row int32 col[k] (padded to 8 / 16 bytes), then
-/// val[k]; `rec` bytes per row (a multiple of 16), PACKED_PAD_ROWS zero records after the last row so whole blocks can always be copied.
+/// Packed copy of an ELL matrix for the staged variant: granules of four consecutive rows, int32 col[4][k] followed by
+/// T val[4][k] -- `gran` = 4 k (4 + sizeof T) bytes, a multiple of 16 for every k and scalar type, values at `valoff` = 16 k
+/// inside the granule; PACKED_PAD_ROWS zero rows after the last row so whole blocks can always be copied.
 constexpr int PACKED_PAD_ROWS = 256;
-void packed_record_layout(int scalar_bytes, int k, uint32_t* rec, uint32_t* valoff);
+void packed_record_layout(int scalar_bytes, int k, uint32_t* gran, uint32_t* valoff);
 size_t packed_ell_bytes(int dtype, EllDev const& h);
 cudaError_t launch_pack_ell(int dtype, EllDev const& h, void* packed, cudaStream_t s);
-/// K1b (kernels_pair.cu): two Chebyshev steps per launch, c = H b - a and d = H c - b, with the four fused sums.
-/// a, b are read, c, d written (four distinct N x R blocks).  `packed2` holds the phase-2 records whose column
-/// entries are codes (>= 0: global row of the tile itself, < 0: -(1 + slot) in the tile's halo list).
-struct PairArgs {
-    const void* packed = nullptr;
-    const void* packed2 = nullptr;
-    const int32_t* halo_ptr = nullptr;   // [tiles + 1]
-    const int32_t* halo_rows = nullptr;  // rows outside a tile that the tile's rows reference, ascending per tile
-    int halo_max = 0;                    // longest halo list
-    const void* a = nullptr; const void* b = nullptr; void* c = nullptr; void* d = nullptr;
-    int64_t nrows = 0;
-    int64_t tile = 0;
-    int R = 1, k = 0;
-    double* partials = nullptr;          // [2][grid][R*C]
-    unsigned* counter = nullptr;         // two counters
-    double* mom = nullptr; double* m01 = nullptr; int M = 0;
-    int n = 0;                           // moments of steps n and n + 1 are written
-    int stages = 4;
-    int blocks_per_sm = 0;
-    int min_blocks = 0;                  // register budget variant: 2 (<= 128 registers) or 3 (<= 80); 0 = by shared memory
-};
-/// *handled == false means "not applicable" (geometry, shared memory): the caller runs two single steps instead.
-cudaError_t launch_step_pair(int dtype, PairArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info, bool* handled);
 /// Upper bound of blocks launch_step may use (size of the partials buffer = this * R * 3 doubles)
 int max_step_blocks(int num_sms);
+
+// ---- device-side construction of a layout from the resident CSR (build.cu) -----------------------
+enum BuildMode : int { BUILD_PLAIN = 0, BUILD_SCALED = 1, BUILD_VELOCITY = 2 };
+struct BuildArgs {
+    const int32_t* indptr = nullptr; const int32_t* indices = nullptr;   // resident CSR (original order, unscaled)
+    int64_t n = 0;
+    const int32_t* queue = nullptr;    // row of the layout -> original site, or null (caller's order)
+    const int32_t* perm = nullptr;     // original site -> row of the layout (with queue)
+    int mode = BUILD_PLAIN;
+    double f = 1.0, sb = 0.0;          // BUILD_SCALED: H~ = (H - sb) * f with the reference's association (see build.cu)
+    const float* positions = nullptr;  // BUILD_VELOCITY: one coordinate per original site
+    int k = 0; int64_t pitch = 0;      // ELL width (launch_row_width) and pitch of the output
+    int32_t* col = nullptr;            // output columns, slot-major; the values go to `val` of launch_csr_to_ell
+};
+int build_max_width();
+/// *out_dev = widest row (+1 where a diagonal entry has to be created by a non-zero b offset)
+cudaError_t launch_row_width(const int32_t* indptr, const int32_t* indices, int64_t n, bool insert_diag, int* out_dev, cudaStream_t s);
+cudaError_t launch_invert_order(const int32_t* queue, int64_t n, int32_t* perm, cudaStream_t s);
+cudaError_t launch_csr_to_ell(int dtype, BuildArgs const& a, const void* data, void* val, cudaStream_t s);
 
 // ---- small helpers -------------------------------------------------------------------------------
 /// dst[i * R + lane] = (i == src[lane]) for lane < nsrc, 0 elsewhere (UnitStarter); dst is zero-filled first

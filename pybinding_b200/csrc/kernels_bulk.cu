@@ -7,7 +7,9 @@
 // operands reach the SM.  Every *streamed* operand of a block-iteration is contiguous in memory:
 //   * y[rows]            -- rpb rows x R lanes, read once and overwritten in place,
 //   * x[rows]            -- the CTA's own rows of the gathered vector (needed for the two dot products),
-//   * H records of rows  -- (col[K], val[K]) of each row, from the row-major *packed* copy of the ELL matrix,
+//   * H records of rows  -- (col[K], val[K]) of each row, from the *packed* copy of the ELL matrix: granules of four
+//                           consecutive rows, int32 col[4][K] then T val[4][K] = 4 K (4 + sizeof T) bytes, always a
+//                           multiple of 16 and exactly the algorithmic size (no padding: 36 bytes per row for c64, K = 3),
 // so thread 0 moves them with three `cp.async.bulk` copies per iteration into a `stages`-deep ring of shared-memory
 // buffers (mbarrier complete_tx signalling; SASS: UBLKCP + SYNCS).  Up to stages x ~8.5 KB per CTA are in flight
 // towards HBM without holding a single register, the warps read y / x / H with conflict-free ld.shared, and the
@@ -29,14 +31,16 @@ namespace pbk {
 namespace {
 
 struct BulkDev {  // kernel parameters
-    const unsigned char* packed;  // row-major H records: int32 col[K] (padded), then T val[K]; `rec` bytes per row
+    const unsigned char* packed;  // granules of 4 rows: int32 col[4][K], then T val[4][K]; `gran` bytes each
     const void* x; void* y;
     int nrows, cpr, rpb, ipt, tile_jump;  // tile_jump: rows to skip to reach this CTA's next tile
-    int R, stages;
-    uint32_t rec, valoff, stage_bytes;
+    int R, stages, k;
+    uint32_t gran, valoff, stage_bytes;   // valoff = 16 K: offset of the values inside a granule
     double* partials; unsigned* counter; double* mom; double* m01; int M; int n; int fin;
 };
 
+// K > 0: ELL width known at compile time (all K gathers of a row in flight together); K == 0: any width, the slots are
+// walked four at a time (same order of the FMAs, so the vectors are bit-identical to the specialised kernels).
 template<class T, int V, int K, bool XS, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) cheb_step_bulk(BulkDev a) {
     using CH = Chunk<T, V>;
@@ -82,12 +86,12 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_bulk(BulkDev a) {
         if (pround > 0) mbar_wait(pfb + empty_off, (pround - 1u) & 1u);  // every warp has read the stage's previous content
         uint32_t const left = lim - pc0;
         uint32_t const vbytes = (left < step_c ? left : step_c) * 16u;
-        uint32_t const hbytes = rpb * a.rec;  // the packed copy is padded: always whole blocks
+        uint32_t const hbytes = (rpb >> 2) * a.gran;  // the packed copy is padded: always whole blocks of granules
         mbar_expect_tx(pfb, (XS ? 2u * vbytes : vbytes) + hbytes);
         bulk_g2s(psb, y + pc0, vbytes, pfb);
         if constexpr (XS) bulk_g2s(psb + HALF, x + pc0, vbytes, pfb);
         else bulk_prefetch_l2(x + pc0, vbytes);
-        bulk_g2s(psb + HOFF, a.packed + static_cast<size_t>(pc0 / cpr) * a.rec, hbytes, pfb);
+        bulk_g2s(psb + HOFF, a.packed + static_cast<size_t>((pc0 / cpr) >> 2) * a.gran, hbytes, pfb);
         pc0 += step_c;
         if (++pw == ipt) { pw = 0; pc0 += jump_c; }
         psb += stage_bytes; pfb += 8u;
@@ -105,8 +109,10 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_bulk(BulkDev a) {
     uint32_t c0 = first_c, sb = smem0, fb = full0, cph = 0;
     int w = 0;
     uint32_t const my_vec = tid * 16u;
-    uint32_t const my_rec = HOFF + ty * a.rec;
-    uint32_t const my_val = my_rec + a.valoff;
+    uint32_t const kk = K > 0 ? static_cast<uint32_t>(K) : static_cast<uint32_t>(a.k);
+    uint32_t const my_gran = HOFF + (ty >> 2) * a.gran;
+    uint32_t const my_rec = my_gran + (ty & 3u) * kk * 4u;                                        // col[ty & 3][0]
+    uint32_t const my_val = my_gran + a.valoff + (ty & 3u) * kk * static_cast<uint32_t>(sizeof(T));  // val[ty & 3][0]
 
     while (c0 < lim) {
         if (tid == 0 && pc0 < lim) produce();  // refill the stage consumed one iteration ago
@@ -117,30 +123,63 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_bulk(BulkDev a) {
         if constexpr (!XS) { if (valid) xr = load_nc(x + ci); }
 
         mbar_wait(fb, cph);
-        int32_t c[K]; T v[K];
-        if (valid) {
-            yv = lds_chunk<CH>(sb + my_vec);
-            if constexpr (XS) xr = lds_chunk<CH>(sb + HALF + my_vec);
+        if constexpr (K > 0) {
+            int32_t c[K]; T v[K];
+            if (valid) {
+                yv = lds_chunk<CH>(sb + my_vec);
+                if constexpr (XS) xr = lds_chunk<CH>(sb + HALF + my_vec);
 #pragma unroll
-            for (int s = 0; s < K; ++s) { c[s] = lds_i32(sb + my_rec + 4u * s); lds_val(sb + my_val + static_cast<uint32_t>(sizeof(T)) * s, v[s]); }
-        }
-        __syncwarp();
-        if ((tid & 31u) == 0) mbar_arrive(fb + empty_off);  // this warp is done with the stage
-
-        if (valid) {
-            CH xg[K];
-#pragma unroll
-            for (int s = 0; s < K; ++s) xg[s] = load_nc(x + (static_cast<uint32_t>(c[s]) * cpr + tx));
-            CH out;
-#pragma unroll
-            for (int e = 0; e < V; ++e) {
-                T r = neg_(yv.e[e]);
-#pragma unroll
-                for (int s = 0; s < K; ++s) r = fma_(v[s], xg[s].e[e], r);
-                out.e[e] = r;
-                sums_(acc + e * C, xr.e[e], r);
+                for (int s = 0; s < K; ++s) { c[s] = lds_i32(sb + my_rec + 4u * s); lds_val(sb + my_val + static_cast<uint32_t>(sizeof(T)) * s, v[s]); }
             }
-            store_cs(y + ci, out);
+            __syncwarp();
+            if ((tid & 31u) == 0) mbar_arrive(fb + empty_off);  // this warp is done with the stage
+
+            if (valid) {
+                CH xg[K];
+#pragma unroll
+                for (int s = 0; s < K; ++s) xg[s] = load_nc(x + (static_cast<uint32_t>(c[s]) * cpr + tx));
+                CH out;
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    T r = neg_(yv.e[e]);
+#pragma unroll
+                    for (int s = 0; s < K; ++s) r = fma_(v[s], xg[s].e[e], r);
+                    out.e[e] = r;
+                    sums_(acc + e * C, xr.e[e], r);
+                }
+                store_cs(y + ci, out);
+            }
+        } else {
+            CH out;
+            if (valid) {
+                yv = lds_chunk<CH>(sb + my_vec);
+                if constexpr (XS) xr = lds_chunk<CH>(sb + HALF + my_vec);
+#pragma unroll
+                for (int e = 0; e < V; ++e) out.e[e] = neg_(yv.e[e]);
+                for (uint32_t s0 = 0; s0 < kk; s0 += 4u) {
+                    int32_t c[4]; T v[4]; CH xg[4];
+#pragma unroll
+                    for (uint32_t j = 0; j < 4u; ++j) {
+                        if (s0 + j < kk) { c[j] = lds_i32(sb + my_rec + 4u * (s0 + j)); lds_val(sb + my_val + static_cast<uint32_t>(sizeof(T)) * (s0 + j), v[j]); }
+                    }
+#pragma unroll
+                    for (uint32_t j = 0; j < 4u; ++j) { if (s0 + j < kk) xg[j] = load_nc(x + (static_cast<uint32_t>(c[j]) * cpr + tx)); }
+#pragma unroll
+                    for (uint32_t j = 0; j < 4u; ++j) {
+                        if (s0 + j < kk) {
+#pragma unroll
+                            for (int e = 0; e < V; ++e) out.e[e] = fma_(v[j], xg[j].e[e], out.e[e]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if ((tid & 31u) == 0) mbar_arrive(fb + empty_off);  // the records were read slot by slot: release the stage now
+            if (valid) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) sums_(acc + e * C, xr.e[e], out.e[e]);
+                store_cs(y + ci, out);
+            }
         }
         c0 += step_c;
         if (++w == ipt) { w = 0; c0 += jump_c; }
@@ -154,14 +193,15 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_bulk(BulkDev a) {
     finish_sums<C, NACC, TPB>(fin, acc, static_cast<int>(tx), static_cast<int>(ty));
 }
 
-// ---- packing: slot-major ELL -> row-major records --------------------------------------------------
+// ---- packing: slot-major ELL -> granules of four rows --------------------------------------------------
 template<class T>
 __global__ void pack_ell_kernel(const T* __restrict__ val, const int32_t* __restrict__ col, int64_t pitch, int k, int64_t rows,
-                                int64_t padded_rows, unsigned char* __restrict__ out, uint32_t rec, uint32_t valoff) {
+                                int64_t padded_rows, unsigned char* __restrict__ out, uint32_t gran, uint32_t valoff) {
     int64_t const row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (row >= padded_rows) return;
-    int32_t* const cp = reinterpret_cast<int32_t*>(out + row * rec);
-    T* const vp = reinterpret_cast<T*>(out + row * rec + valoff);
+    unsigned char* const g = out + (row >> 2) * gran;
+    int32_t* const cp = reinterpret_cast<int32_t*>(g) + (row & 3) * k;
+    T* const vp = reinterpret_cast<T*>(g + valoff) + (row & 3) * k;
     for (int s = 0; s < k; ++s) {
         bool const in = row < rows;
         cp[s] = in ? col[s * pitch + row] : 0;
@@ -205,7 +245,7 @@ BulkKernel bulk_kernel_k(int k) {
         case 3: return cheb_step_bulk<T, V, 3, XS, BULK_TPB, 4>;
         case 4: return cheb_step_bulk<T, V, 4, XS, BULK_TPB, 4>;
         case 7: return cheb_step_bulk<T, V, 7, XS, BULK_TPB, 4>;
-        default: return nullptr;
+        default: return cheb_step_bulk<T, V, 0, XS, BULK_TPB, 4>;   // any other width (next-nearest neighbours, several orbitals ...)
     }
 }
 
@@ -216,10 +256,10 @@ cudaError_t launch_bulk_t(StepArgs const& a, int num_sms, cudaStream_t stream, L
     if (a.R % V != 0) return cudaSuccess;
     int const cpr = a.R / V;
     if (cpr > BULK_TPB) return cudaSuccess;
-    int const rpb = BULK_TPB / cpr;
-    uint32_t rec = 0, valoff = 0;
-    packed_record_layout(sizeof(T), a.h.k, &rec, &valoff);
-    if ((static_cast<uint32_t>(rpb) * rec) % 16u != 0 || rpb > PACKED_PAD_ROWS) return cudaSuccess;
+    int const rpb = (BULK_TPB / cpr) & ~3;   // whole granules of four rows per block-iteration (threads beyond rpb * cpr idle)
+    uint32_t gran = 0, valoff = 0;
+    packed_record_layout(sizeof(T), a.h.k, &gran, &valoff);
+    if (rpb < 4 || rpb > PACKED_PAD_ROWS) return cudaSuccess;   // a block-iteration copies whole granules of four rows
     int ipt = 1;
     if (a.tile > rpb) ipt = static_cast<int>((a.tile + rpb - 1) / rpb);
     int64_t const tile_rows = static_cast<int64_t>(ipt) * rpb;
@@ -230,7 +270,7 @@ cudaError_t launch_bulk_t(StepArgs const& a, int num_sms, cudaStream_t stream, L
 
     int const stages = a.bulk_stages > 16 ? 16 : a.bulk_stages;
     uint32_t const hoff = BULK_TPB * 16u * (a.bulk_xstage ? 2u : 1u);
-    uint32_t const stage_bytes = hoff + (static_cast<uint32_t>(rpb) * rec + 127u) / 128u * 128u;
+    uint32_t const stage_bytes = hoff + (static_cast<uint32_t>(rpb / 4) * gran + 127u) / 128u * 128u;
     int const dyn = static_cast<int>(stages * stage_bytes + 16u * stages);
     if (dyn > BULK_MAX_DYN) return cudaSuccess;
     int64_t const need = (a.nrows + tile_rows - 1) / tile_rows;
@@ -248,7 +288,7 @@ cudaError_t launch_bulk_t(StepArgs const& a, int num_sms, cudaStream_t stream, L
     d.x = a.x; d.y = a.y;
     d.nrows = static_cast<int>(a.nrows); d.cpr = cpr; d.rpb = rpb; d.ipt = ipt;
     d.tile_jump = static_cast<int>((grid - 1) * tile_rows);
-    d.R = a.R; d.stages = stages; d.rec = rec; d.valoff = valoff; d.stage_bytes = stage_bytes;
+    d.R = a.R; d.stages = stages; d.k = a.h.k; d.gran = gran; d.valoff = valoff; d.stage_bytes = stage_bytes;
     d.partials = a.partials; d.counter = a.counter; d.mom = a.mom; d.m01 = a.m01; d.M = a.M; d.n = a.n; d.fin = a.fin;
     fn<<<grid, BULK_TPB, dyn, stream>>>(d);
     *handled = true;
@@ -258,23 +298,21 @@ cudaError_t launch_bulk_t(StepArgs const& a, int num_sms, cudaStream_t stream, L
 
 } // anonymous namespace
 
-void packed_record_layout(int scalar_bytes, int k, uint32_t* rec, uint32_t* valoff) {
-    uint32_t const align = scalar_bytes >= 16 ? 16u : 8u;
-    uint32_t const vo = (4u * k + align - 1u) / align * align;
-    *valoff = vo;
-    *rec = (vo + static_cast<uint32_t>(scalar_bytes) * k + 15u) / 16u * 16u;  // whole 16-byte units: any row count is a valid bulk copy
+void packed_record_layout(int scalar_bytes, int k, uint32_t* gran, uint32_t* valoff) {
+    *valoff = 16u * static_cast<uint32_t>(k);                                       // int32 col[4][k]
+    *gran = 4u * static_cast<uint32_t>(k) * (4u + static_cast<uint32_t>(scalar_bytes));   // + T val[4][k]: a multiple of 16 for every k
 }
 
 size_t packed_ell_bytes(int dtype, EllDev const& h) {
-    uint32_t rec = 0, valoff = 0;
-    packed_record_layout(dtype_size(dtype), h.k, &rec, &valoff);
-    return static_cast<size_t>(h.rows + PACKED_PAD_ROWS) * rec;
+    uint32_t gran = 0, valoff = 0;
+    packed_record_layout(dtype_size(dtype), h.k, &gran, &valoff);
+    return static_cast<size_t>((h.rows + PACKED_PAD_ROWS + 3) / 4) * gran;
 }
 
 cudaError_t launch_pack_ell(int dtype, EllDev const& h, void* packed, cudaStream_t s) {
     uint32_t rec = 0, valoff = 0;
     packed_record_layout(dtype_size(dtype), h.k, &rec, &valoff);
-    int64_t const padded = h.rows + PACKED_PAD_ROWS;
+    int64_t const padded = (h.rows + PACKED_PAD_ROWS + 3) / 4 * 4;
     int const grid = static_cast<int>((padded + 255) / 256);
     auto* out = static_cast<unsigned char*>(packed);
     switch (dtype) {

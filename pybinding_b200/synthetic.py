@@ -28,12 +28,14 @@ from dataclasses import dataclass, field
 import numpy as np
 import scipy.sparse as sp
 
-__all__ = ["Model", "System", "Positions", "Rectangle", "graphene_rectangle", "cubic_anderson",
-           "GRAPHENE_A", "GRAPHENE_ACC", "GRAPHENE_T"]
+__all__ = ["Model", "System", "Positions", "Rectangle", "Polygon", "graphene_rectangle", "cubic_anderson",
+           "lattice_model", "graphene_monolayer", "graphene_hexagon_ac", "mos2_3band",
+           "GRAPHENE_A", "GRAPHENE_ACC", "GRAPHENE_T", "GRAPHENE_T_NN"]
 
 GRAPHENE_A = 0.24595    # [nm] unit cell length
 GRAPHENE_ACC = 0.142    # [nm] carbon-carbon distance
 GRAPHENE_T = -2.8       # [eV] nearest neighbour hopping
+GRAPHENE_T_NN = 0.1     # [eV] next-nearest neighbour hopping (pybinding/repository/graphene/constants.py:6)
 _HBAR = 6.58211899e-16  # [eV*s]  (pybinding/constants.py)
 _PHI0 = 2 * math.pi * _HBAR
 
@@ -66,15 +68,32 @@ class Rectangle:
         return _within_polygon(np.asarray(x, np.float32), np.asarray(y, np.float32), self.vertices)
 
 
-class System:
-    """Positions + sublattice bookkeeping (single-orbital sites)"""
+class Polygon:
+    """Minimal stand-in for `pb.Polygon` (pybinding/shape.py): vertices + `lattice_offset` + `contains`"""
 
-    def __init__(self, x, y, z, sub_starts, sub_names):
+    def __init__(self, vertices, lattice_offset=(0.0, 0.0)):
+        self.vertices = [tuple(float(c) for c in v[:2]) for v in vertices]
+        self.lattice_offset = tuple(lattice_offset)
+
+    def contains(self, x, y, z=None):
+        return _within_polygon(np.asarray(x, np.float32), np.asarray(y, np.float32), self.vertices)
+
+
+class System:
+    """Positions + sublattice bookkeeping.  `orbitals[i]` = number of orbitals of sublattice i (default 1): the
+    Hamiltonian rows of a site are consecutive, sublattice blocks follow each other
+    (System::to_hamiltonian_indices / hamiltonian_size / expanded_positions, cppcore/src/system/System.cpp:8-97)"""
+
+    def __init__(self, x, y, z, sub_starts, sub_names, orbitals=None):
         self.positions = Positions(np.ascontiguousarray(x, np.float32),
                                    np.ascontiguousarray(y, np.float32),
                                    np.ascontiguousarray(z, np.float32))
         self._sub_starts = list(sub_starts)  # len = nsub + 1
         self._sub_names = list(sub_names)
+        self._orbitals = list(orbitals) if orbitals is not None else [1] * len(self._sub_names)
+        self._ham_starts = [0]
+        for i, norb in enumerate(self._orbitals):
+            self._ham_starts.append(self._ham_starts[-1] + norb * (self._sub_starts[i + 1] - self._sub_starts[i]))
 
     @property
     def num_sites(self):
@@ -82,11 +101,20 @@ class System:
 
     @property
     def hamiltonian_size(self):
-        return self.num_sites
+        return int(self._ham_starts[-1])
+
+    @property
+    def is_multiorbital(self):
+        return any(norb > 1 for norb in self._orbitals)
 
     @property
     def expanded_positions(self):
-        return self.positions
+        if not self.is_multiorbital:
+            return self.positions
+        reps = np.concatenate([np.full(self._sub_starts[i + 1] - self._sub_starts[i], norb, np.int64)
+                               for i, norb in enumerate(self._orbitals)])
+        return Positions(np.repeat(self.positions.x, reps), np.repeat(self.positions.y, reps),
+                         np.repeat(self.positions.z, reps))
 
     @property
     def x(self):
@@ -120,7 +148,11 @@ class System:
         return int(start + np.argmin(d))
 
     def to_hamiltonian_indices(self, system_index):
-        return np.array([system_index], dtype=np.int32)
+        for i, norb in enumerate(self._orbitals):
+            if self._sub_starts[i] <= system_index < self._sub_starts[i + 1]:
+                first = self._ham_starts[i] + (system_index - self._sub_starts[i]) * norb
+                return np.arange(first, first + norb, dtype=np.int32)
+        raise IndexError("to_hamiltonian_indices: site index out of range")
 
 
 @dataclass
@@ -143,7 +175,7 @@ class Model:
 
     @property
     def is_multiorbital(self):
-        return False
+        return bool(getattr(self.system, "is_multiorbital", False))
 
     @property
     def raw_hamiltonian(self):
@@ -376,3 +408,201 @@ def cubic_anderson(length, *, disorder=4.0, seed=0, t=-1.0, periodic=True, dtype
     system = System(xx.ravel(), yy.ravel(), zz.ravel(), [0, n], ["A"])
     return Model(h, system, "simple cubic Anderson {}^3, W={}".format(L, disorder),
                  dict(length=L, disorder=disorder, periodic=periodic, volume=float(n)))
+
+
+# ------------------------------------------------------------------------------------------------
+# Generic 2-D lattice + polygon builder: the models of the reference's own KPM / sweep tests that are not
+# nearest-neighbour graphene rectangles (tests/test_kpm.py:23 `group6_tmd.monolayer_3band("MoS2")`,
+# tests/test_parallel.py:16-52 `graphene.hexagon_ac`) and lattices with other ELL widths (next-nearest-neighbour
+# graphene).  Same conventions as `graphene_rectangle` above, written for clarity rather than for 38 M sites.
+# ------------------------------------------------------------------------------------------------
+def _as_matrix(energy, rows, cols=None):
+    """Scalar / 1-D list (diagonal) / 2-D list -> matrix, like Lattice.add_one_sublattice / add_one_hopping"""
+    e = np.atleast_1d(np.asarray(energy))
+    if e.ndim == 1:
+        if e.size == 1 and rows == 1:
+            return e.reshape(1, 1)
+        return np.diag(e)
+    return e
+
+
+def lattice_model(a1, a2, sublattices, hoppings, shape, *, min_neighbors=1, onsite=0.0, magnetic_field=0.0,
+                  dtype=None, description=""):
+    """`pb.Model(lattice, shape [, pb.constant_potential(onsite)] [, constant_magnetic_field(B)])` as CSR + positions
+
+    Parameters
+    ----------
+    a1, a2 : (x, y) primitive vectors [nm]
+    sublattices : list of (name, (x, y) offset, onsite energy: scalar, list (diagonal) or matrix)
+    hoppings : list of ((da, db), from_name, to_name, energy: scalar or matrix with rows = orbitals of `from`)
+        One entry per `Lattice.add_hoppings` term; the conjugate is added automatically
+        (Hamiltonian.hpp:85-88: H(i, j) = t, H(j, i) = conj(t) with j = the site at i + (da, db)).
+    shape : object with `.vertices` and optional `.lattice_offset` (`Polygon`, `Rectangle`)
+    """
+    f32 = np.float32
+    a1 = np.array(a1, f32)
+    a2 = np.array(a2, f32)
+    names = [sub[0] for sub in sublattices]
+    norbs = [int(_as_matrix(sub[2], 1).shape[0]) if np.ndim(sub[2]) > 0 else 1 for sub in sublattices]
+    order = sorted(range(len(names)), key=lambda i: norbs[i])      # OptimizedUnitCell: stable sort by orbital count
+    sublattices = [sublattices[i] for i in order]
+    names = [names[i] for i in order]
+    norbs = [norbs[i] for i in order]
+    nsub = len(names)
+    vertices = [tuple(v[:2]) for v in shape.vertices]
+    offset = np.array(getattr(shape, "lattice_offset", (0.0, 0.0))[:2], f32)
+
+    lat = np.array([[a1[0], a2[0]], [a1[1], a2[1]]], np.float64)
+    v = np.array([np.linalg.solve(lat, np.array(p, np.float64)).astype(f32) for p in vertices])
+    v = np.trunc(v).astype(np.int64)
+    lower = v.min(axis=0) - 1
+    upper = v.max(axis=0) + 1
+    size0, size1 = (upper - lower + 1).tolist()
+
+    origin = offset + f32(lower[0]) * a1 + f32(lower[1]) * a2      # Lattice::calc_position(bounds.first)
+    ia = np.arange(size0, dtype=f32)
+    ib = np.arange(size1, dtype=f32)
+    px = np.empty((nsub, size1, size0), f32)
+    py = np.empty((nsub, size1, size0), f32)
+    for n in range(nsub):
+        ps = origin + np.array(sublattices[n][1][:2], f32)
+        pbx = np.where(ib == 0, ps[0], ps[0] + ib * a2[0]).astype(f32)
+        pby = np.where(ib == 0, ps[1], ps[1] + ib * a2[1]).astype(f32)
+        px[n] = pbx[:, None] + ia[None, :] * a1[0]
+        py[n] = pby[:, None] + ia[None, :] * a1[1]
+    valid = _within_polygon(px.ravel(), py.ravel(), vertices).reshape(nsub, size1, size0)
+
+    def shifted(arr, da, db, fill):
+        out = np.full(arr.shape, fill, arr.dtype)
+        sb = slice(max(0, -db), arr.shape[0] - max(0, db))
+        sa = slice(max(0, -da), arr.shape[1] - max(0, da))
+        tb = slice(max(0, db), arr.shape[0] - max(0, -db))
+        ta = slice(max(0, da), arr.shape[1] - max(0, -da))
+        out[sb, sa] = arr[tb, ta]
+        return out
+
+    terms = [((int(rel[0]), int(rel[1])), names.index(fr), names.index(to), en) for rel, fr, to, en in hoppings]
+    while True:  # remove_dangling fix point (Foundation.cpp:51-101): hoppings and their conjugates both count
+        counts = [np.zeros((size1, size0), np.int32) for _ in range(nsub)]
+        for (da, db), fr, to, _ in terms:
+            counts[fr] += shifted(valid[to], da, db, False)
+            counts[to] += shifted(valid[fr], -da, -db, False)
+        new = np.stack([valid[n] & (counts[n] >= min_neighbors) for n in range(nsub)])
+        if new.sum() == valid.sum():
+            break
+        valid = new
+
+    flat_valid = valid.ravel()
+    n_sites = int(flat_valid.sum())
+    index = np.full(flat_valid.size, -1, np.int64)
+    index[flat_valid] = np.arange(n_sites)
+    index = index.reshape(nsub, size1, size0)
+    sub_starts = [0]
+    for n in range(nsub):
+        sub_starts.append(sub_starts[-1] + int(valid[n].sum()))
+    ham_starts = [0]
+    for n in range(nsub):
+        ham_starts.append(ham_starts[-1] + norbs[n] * (sub_starts[n + 1] - sub_starts[n]))
+    x = px.ravel()[flat_valid]
+    y = py.ravel()[flat_valid]
+
+    is_complex = magnetic_field != 0 or any(np.iscomplexobj(np.asarray(t[3])) for t in terms) \
+        or any(np.iscomplexobj(np.asarray(sub[2])) for sub in sublattices)
+    dtype = _resolve_dtype(dtype, is_complex, False)
+    if is_complex and dtype.kind != "c":
+        raise ValueError("complex terms require a complex dtype")
+    real_dtype = np.dtype(np.float32 if dtype in (np.float32, np.complex64) else np.float64)
+
+    def ham_index(sub, site, orbital):
+        return ham_starts[sub] + (site - sub_starts[sub]) * norbs[sub] + orbital
+
+    rows, cols, vals = [], [], []
+    for n in range(nsub):   # onsite terms; zeros are not stored (HamiltonianModifiers.hpp:149)
+        energy = _as_matrix(sublattices[n][2], norbs[n]).astype(dtype) + np.eye(norbs[n], dtype=dtype) * dtype.type(onsite)
+        sites = np.arange(sub_starts[n], sub_starts[n + 1])
+        for p in range(norbs[n]):
+            for q in range(norbs[n]):
+                if energy[p, q] != 0:
+                    rows.append(ham_index(n, sites, p)); cols.append(ham_index(n, sites, q))
+                    vals.append(np.full(sites.size, energy[p, q], dtype))
+    const = real_dtype.type(1e-18 * 2 * math.pi / _PHI0)
+    for (da, db), fr, to, energy in terms:
+        src = index[fr]
+        dst = shifted(index[to], da, db, -1)
+        ok = (src >= 0) & (dst >= 0)
+        i_site, j_site = src[ok], dst[ok]
+        h = _as_matrix(energy, norbs[fr], norbs[to]).astype(dtype)
+        phase = None
+        if magnetic_field != 0:
+            x1, y1 = x[i_site].astype(real_dtype), y[i_site].astype(real_dtype)
+            x2, y2 = x[j_site].astype(real_dtype), y[j_site].astype(real_dtype)
+            peierls = (real_dtype.type(0.5 * magnetic_field) * (y1 + y2)) * (x1 - x2)
+            phase = np.exp(1j * (const * peierls)).astype(dtype)
+        for p in range(norbs[fr]):
+            for q in range(norbs[to]):
+                if h[p, q] == 0:
+                    continue
+                value = np.full(i_site.size, h[p, q], dtype) if phase is None else (h[p, q] * phase).astype(dtype)
+                r, c = ham_index(fr, i_site, p), ham_index(to, j_site, q)
+                rows += [r, c]; cols += [c, r]; vals += [value, np.conj(value)]
+    size = ham_starts[-1]
+    coo = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(size, size))
+    h = coo.tocsr()
+    h.sort_indices()
+    h = sp.csr_matrix((h.data.astype(dtype), h.indices.astype(np.int32), h.indptr.astype(np.int32)), shape=(size, size))
+    h.has_sorted_indices = True
+    system = System(x, y, np.zeros(n_sites, f32), sub_starts, names, norbs)
+    return Model(h, system, description, dict(onsite=onsite, magnetic_field=magnetic_field, min_neighbors=min_neighbors))
+
+
+def graphene_monolayer(shape, *, nearest_neighbors=1, onsite=0.0, magnetic_field=0.0, dtype=None, t=GRAPHENE_T,
+                       t_nn=GRAPHENE_T_NN):
+    """`graphene.monolayer(nearest_neighbors)` (pybinding/repository/graphene/lattice.py:6-66) on any polygon
+
+    nearest_neighbors = 2 adds the six second-neighbour hoppings and the 3 t_nn onsite offset: 3 + 6 + 1 = 10 entries
+    per row, a lattice outside the specialised ELL widths of the step kernels."""
+    a, acc = GRAPHENE_A, GRAPHENE_ACC
+    offset = 0.0 if nearest_neighbors < 2 else 3 * t_nn
+    subs = [("A", (0.0, -acc / 2), offset), ("B", (0.0, acc / 2), offset)]
+    hops = [((0, 0), "A", "B", t), ((1, -1), "A", "B", t), ((0, -1), "A", "B", t)]
+    if nearest_neighbors >= 2:
+        for rel in ((0, -1), (1, -1), (1, 0)):
+            hops += [(rel, "A", "A", t_nn), (rel, "B", "B", t_nn)]
+    if nearest_neighbors >= 3:
+        raise ValueError("nearest_neighbors > 2 is not provided")
+    return lattice_model([a, 0.0], [a / 2, a / 2 * math.sqrt(3.0)], subs, hops, shape, min_neighbors=2, onsite=onsite,
+                         magnetic_field=magnetic_field, dtype=dtype,
+                         description="graphene.monolayer(nearest_neighbors={})".format(nearest_neighbors))
+
+
+def graphene_hexagon_ac(side_width, lattice_offset=(-GRAPHENE_A / 2, 0.0)):
+    """`graphene.hexagon_ac(side_width)` (pybinding/repository/graphene/shape.py:8-34): armchair edges on all sides"""
+    side_atoms = math.ceil((side_width / GRAPHENE_ACC + 1) * 2 / 3)
+    side_atoms += side_atoms % 2
+    side_width = (3 / 2 * side_atoms - 1) * GRAPHENE_ACC - GRAPHENE_ACC / 2
+    x0 = side_width * math.sqrt(3) / 2
+    y0 = side_width
+    return Polygon([(0, y0), (x0, y0 / 2), (x0, -y0 / 2), (0, -y0), (-x0, -y0 / 2), (-x0, y0 / 2)], lattice_offset)
+
+
+def mos2_3band(shape, name="MoS2", dtype=None):
+    """`group6_tmd.monolayer_3band(name)` (pybinding/repository/group6_tmd.py:19-113): one metal sublattice with three
+    orbitals on a triangular lattice, 3 x 3 hopping matrices to the six neighbours (ELL width 21)"""
+    params = {"MoS2": [0.3190, 1.046, 2.104, -0.184, 0.401, 0.507, 0.218, 0.338, 0.057],
+              "WS2": [0.3191, 1.130, 2.275, -0.206, 0.567, 0.536, 0.286, 0.384, -0.061]}
+    a, eps1, eps2, t0, t1, t2, t11, t12, t22 = params[name]
+    rt3 = math.sqrt(3)
+    h1 = [[t0, -t1, t2],
+          [t1, t11, -t12],
+          [t2, t12, t22]]
+    h2 = [[t0, 1 / 2 * t1 + rt3 / 2 * t2, rt3 / 2 * t1 - 1 / 2 * t2],
+          [-1 / 2 * t1 + rt3 / 2 * t2, 1 / 4 * t11 + 3 / 4 * t22, rt3 / 4 * (t11 - t22) - t12],
+          [-rt3 / 2 * t1 - 1 / 2 * t2, rt3 / 4 * (t11 - t22) + t12, 3 / 4 * t11 + 1 / 4 * t22]]
+    h3 = [[t0, -1 / 2 * t1 - rt3 / 2 * t2, rt3 / 2 * t1 - 1 / 2 * t2],
+          [1 / 2 * t1 - rt3 / 2 * t2, 1 / 4 * t11 + 3 / 4 * t22, rt3 / 4 * (t22 - t11) + t12],
+          [-rt3 / 2 * t1 - 1 / 2 * t2, rt3 / 4 * (t22 - t11) - t12, 3 / 4 * t11 + 1 / 4 * t22]]
+    metal = name[:2] if name[1].islower() else name[:1]
+    subs = [(metal, (0.0, 0.0), [eps1, eps2, eps2])]
+    hops = [((1, 0), metal, metal, h1), ((0, -1), metal, metal, h2), ((1, -1), metal, metal, h3)]
+    return lattice_model([a, 0.0], [a / 2, rt3 / 2 * a], subs, hops, shape, min_neighbors=1, dtype=dtype,
+                         description="group6_tmd.monolayer_3band({})".format(name))

@@ -307,3 +307,57 @@ def test_pybind11_binding_equals_ctypes_binding():
     b.model = pb.graphene_rectangle(8)     # cpb::KPM::set_model: new Hamiltonian, same object
     assert b.system.num_sites == pb.graphene_rectangle(8).system.num_sites
     assert np.array_equal(b.calc_dos(energy, 0.3, 2).data, pb.kpm(pb.graphene_rectangle(8), energy_range=(-9, 9), silent=True).calc_dos(energy, 0.3, 2).data)
+
+
+# ---- models outside nearest-neighbour graphene: other ELL widths, several orbitals per site --------------------------
+def test_reference_golden_ldos_mos2_three_orbitals(golden):
+    """tests/test_kpm.py:23-47 for `group6_tmd.monolayer_3band("MoS2")`: LDOS per orbital (reduce=False) against the
+    reference's baseline, and the orbital sum (reduce=True, KPM.cpp:64) -- ELL width 19, three Hamiltonian rows per site"""
+    from pybinding_b200 import synthetic as syn
+    model = syn.mos2_3band(pb.Rectangle(6))
+    energy = np.linspace(0, 2, 25)
+    for optimal_size in (True, False):
+        for binding in ("ctypes", "pybind11"):
+            kpm = pb.kpm(model, kernel=pb.lorentz_kernel(), silent=True, optimal_size=optimal_size, binding=binding)
+            ldos = kpm.calc_ldos(energy, broadening=0.15, position=[0, 0.07], reduce=False)
+            assert ldos.data.shape == (25, 3)
+            assert np.allclose(ldos.data, golden["ldos[mos2]"], rtol=1e-3, atol=1e-6)
+            total = kpm.calc_ldos(energy, broadening=0.15, position=[0, 0.07])
+            assert total.data.shape == (25,) and np.allclose(total.data, ldos.data.sum(axis=1), rtol=1e-6)
+    with pytest.raises(RuntimeError, match="multi-orbital"):
+        kpm.calc_spatial_ldos(energy, 0.15, pb.Rectangle(1.0))
+    # conductivity uses the positions expanded per orbital (KPM.cpp:140)
+    sigma = pb.kpm(model, energy_range=(-4, 6), kernel=pb.lorentz_kernel(), silent=True) \
+        .calc_conductivity(np.linspace(-1, 1, 5), broadening=0.5, temperature=300, num_random=1, num_points=60)
+    ref = OracleKPM(model.hamiltonian, energy_range=(-4, 6), kernel="lorentz", hp=True)
+    xs = model.system.expanded_positions.x
+    expected = ref.calc_conductivity(np.linspace(-1, 1, 5), 0.5, 300, xs, xs, num_random=1, num_points=60)
+    assert rel_err(sigma.data, expected) < 2e-4
+
+
+@pytest.mark.parametrize("name", ["nnn_graphene_f32", "nnn_graphene_c128", "mos2_f32", "mos2_f64"])
+def test_generic_ell_widths_match_the_oracle(name):
+    """Lattices whose ELL width is not one of the nearest-neighbour cases (3, 4, 7): next-nearest-neighbour graphene
+    (10 per row, 11 with the b offset) and the three-band TMD model (19 / 20); DOS, LDOS, Green's and generic moments"""
+    from pybinding_b200 import synthetic as syn
+    if name.startswith("nnn"):
+        dtype = np.dtype(np.float32 if name.endswith("f32") else np.complex128)
+        model = syn.graphene_monolayer(pb.Rectangle(9.0), nearest_neighbors=2, dtype=dtype,
+                                       magnetic_field=300.0 if dtype.kind == "c" else 0.0)
+        er = (-9.2, 9.6)
+    else:
+        dtype = np.dtype(np.float32 if name.endswith("f32") else np.float64)
+        model = syn.mos2_3band(pb.Rectangle(14.0), dtype=dtype)
+        er = (-3.5, 6.5)
+    kpm = pb.kpm(model, energy_range=er, silent=True)
+    ref = OracleKPM(model.hamiltonian, energy_range=er, hp=True)
+    tol = TOL[dtype]
+    for R in (1, 5, 16):
+        assert rel_err(kpm.impl.moments_dos(130, R), ref.dos_moments(130, R)) < tol
+    n = model.hamiltonian.shape[0]
+    idx = [n // 2, n // 3, n // 2 + 1]
+    assert rel_err(kpm.impl.moments_ldos(98, idx), ref.ldos_moments(98, idx)) < tol
+    assert rel_err(kpm.impl.moments_ldos(98, idx[:1]), ref.ldos_moments(98, idx[:1])) < tol
+    assert rel_err(kpm.impl.moments_greens(98, idx[0], idx), ref.greens_moments(98, idx[0], idx)) < tol
+    x = model.system.expanded_positions.x
+    assert rel_err(kpm.impl.moments_kubo(34, x, x, 1), ref.kubo_moments(34, x, x, 1)) < tol * 5

@@ -23,8 +23,8 @@ pytestmark = pytest.mark.gpu
 
 TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.complex64): 1e-5,
        np.dtype(np.float64): 1e-11, np.dtype(np.complex128): 1e-11}
-KNOBS = ("PBK_BULK", "PBK_XS", "PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL",
-         "PBK_PAIR", "PBK_PAIR_STAGES", "PBK_PAIR_MINB", "PBK_PAIR_R", "PBK_CONE",
+KNOBS = ("PBK_DEVBUILD", "PBK_BULK", "PBK_XS", "PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL",
+         "PBK_CONE",
          "PBK_GRAPH", "PBK_GRAPH_MAX_MB")
 
 
@@ -85,56 +85,6 @@ def test_bulk_kernel_matches_general_kernel_and_oracle(dtype, k):
         assert rel_err(staged, expected) < TOL[dtype], kw
         # same arithmetic per row; only the per-thread partition of the f64 sums differs (f32 vectors: ~1e-8)
         assert rel_err(staged, general) < (1e-12 if dtype.itemsize >= 8 and dtype != np.complex64 else 1e-6), kw
-
-
-@pytest.mark.parametrize("k", [3, 4, 7])
-@pytest.mark.parametrize("dtype", [np.float32, np.complex64, np.float64, np.complex128], ids=lambda d: np.dtype(d).name)
-def test_pair_kernel_matches_single_step_kernel_and_oracle(dtype, k):
-    """Two Chebyshev steps per launch (cheb_pair_bulk, kernels_pair.cu) against one step per launch and the oracle;
-    M = 68 leaves an odd number of steps, so the run ends with one single-step launch."""
-    dtype = np.dtype(dtype)
-    model, er = model_for(dtype, k)
-    R = 12
-    for M in (66, 68):
-        single, s0 = dos_moments(model, er, M, R, PBK_PAIR=0)
-        assert s0.pair_launches == 0
-        # the oracle (like the reference) only takes 4k + 2 moments; M = 68 is checked against the single-step kernel
-        expected = OracleKPM(model.hamiltonian, energy_range=er, hp=True).dos_moments(M, R) if M % 4 == 2 else single
-        steps = M // 2 - 1
-        for kw in (dict(PBK_PAIR=2), dict(PBK_PAIR=2, PBK_PAIR_MINB=2), dict(PBK_PAIR=2, PBK_PAIR_STAGES=2, PBK_TILE=64),
-                   dict(PBK_PAIR=2, PBK_PAIR_STAGES=7, PBK_TILE=96, PBK_PAIR_MINB=3)):
-            pair, s1 = dos_moments(model, er, M, R, **kw)
-            assert s1.pair_launches == steps // 2, "the two-step kernel did not run: {}".format(kw)
-            assert s1.step_launches == 1 + steps // 2 + steps % 2
-            assert rel_err(pair, expected) < TOL[dtype], kw
-            # the vectors are bit-identical to single steps; only the partition of the f64 sums over threads differs
-            assert rel_err(pair, single) < (1e-12 if dtype.itemsize >= 8 and dtype != np.complex64 else 1e-6), kw
-
-
-@pytest.mark.parametrize("R", [2, 5, 8, 33, 64])
-def test_pair_kernel_lane_counts(R):
-    model = pb.graphene_rectangle(12.0, dtype=np.complex64, magnetic_field=300.0)
-    M = 38
-    single, _ = dos_moments(model, (-9, 9), M, R, PBK_PAIR=0)
-    pair, s = dos_moments(model, (-9, 9), M, R, PBK_PAIR=1)
-    assert s.pair_launches == (M // 2 - 1) // 2
-    assert rel_err(pair, single) < 1e-6
-
-
-def test_pair_kernel_at_size_is_reproducible_and_matches_single_steps():
-    model = pb.graphene_rectangle(60.0, dtype=np.complex64, magnetic_field=100.0)   # 137 k sites, 537 tiles
-    M, R = 130, 16
-    single, _ = dos_moments(model, (-8.5, 8.5), M, R, PBK_PAIR=0)
-    pair, s = dos_moments(model, (-8.5, 8.5), M, R, PBK_PAIR=1)
-    assert s.pair_launches == 32
-    again, _ = dos_moments(model, (-8.5, 8.5), M, R, PBK_PAIR=1)
-    assert np.array_equal(pair, again), "moments must be bit-reproducible run to run"
-    assert np.abs(pair - single).max() / np.abs(single).max() < 2e-6
-    f64 = pb.graphene_rectangle(40.0, dtype=np.float64, onsite=0.2)
-    a, _ = dos_moments(f64, (-9, 9), 98, 6, PBK_PAIR=0)
-    b, s = dos_moments(f64, (-9, 9), 98, 6, PBK_PAIR=1, max_batch=0)
-    assert s.pair_launches == 24
-    assert np.abs(a - b).max() / np.abs(a).max() < 1e-12
 
 
 @pytest.mark.parametrize("R", [1, 2, 5, 8, 33, 64])
@@ -299,3 +249,25 @@ def test_graph_replay_of_small_recursions_is_bit_identical():
         k2 = pb.kpm(big, energy_range=(-8.5, 8.5), silent=True)
         k2.impl.moments_dos(66, 16)
         assert k2.stats.graph_launches == 0      # 137 k sites x 16 vectors x 8 bytes = 17.6 MB > 1 MB: plain launches
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.complex64, np.float64, np.complex128], ids=lambda d: np.dtype(d).name)
+def test_layouts_built_on_the_device_equal_the_host_build(dtype):
+    """build.cu (CSR -> scaled, relabelled ELL by one kernel) against the host restatement of create_scaled /
+    create_reordered (bit-identical to the oracle: tests/test_host_ell.py): the same matrix bits give the same moments
+    bit for bit -- full-system locality layout with b != 0 (inserted diagonal), breadth-first layout (Green's), unscaled
+    layout (Lanczos bounds) and the velocity operators (Kubo-Bastin)"""
+    dtype = np.dtype(dtype)
+    model = pb.graphene_rectangle(9.0, onsite=0.3 if dtype != np.float32 else 0.0, dtype=dtype,
+                                  magnetic_field=400.0 if dtype.kind == "c" else 0.0)
+    n = model.system.num_sites
+    results = []
+    for dev in (1, 0):
+        with knobs(PBK_DEVBUILD=dev, PBK_CONE=0):
+            kpm = pb.kpm(model, energy_range=(-9.1, 9.3), silent=True)
+            auto = pb.kpm(model, silent=True)
+            results.append(dict(dos=kpm.impl.moments_dos(66, 5), greens=kpm.impl.moments_greens(50, n // 2, [n // 3, n // 2 + 3]),
+                                ldos=kpm.impl.moments_ldos(50, [n // 4]), bounds=auto.impl.bounds,
+                                kubo=kpm.impl.moments_kubo(18, model.system.x, model.system.y, 1)))
+    for key in results[0]:
+        assert np.array_equal(np.asarray(results[0][key]), np.asarray(results[1][key])), key

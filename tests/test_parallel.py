@@ -112,3 +112,37 @@ def test_deferred_ldos_sweep_on_the_gpu_equals_sequential():
     for i, x in enumerate(xs):
         expected = one.calc_ldos(energy, broadening=0.1, position=[x, 0.5]).data
         assert np.array_equal(result.data[i], expected)
+
+
+@pytest.mark.gpu
+def test_reference_sweep_goldens_on_the_gpu():
+    """The reference's own sweep tests (tests/test_parallel.py:16-52) against its own baselines
+    (tests/baseline_data/parallel/{sweep,ndsweep}.pbz -> tests/golden/reference_parallel_baselines.npz): deferred LDOS of
+    a graphene armchair hexagon in a constant potential, through parallelize / sweep / ndsweep, reference tolerances."""
+    import os
+    import pybinding_b200 as pb
+    from pybinding_b200 import synthetic as syn
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_parallel_baselines.npz"))
+    shape = syn.graphene_hexagon_ac(side_width=15)
+
+    @parallel.parallelize(v=np.linspace(0, 0.1, 10))
+    def factory(v, energy=np.linspace(0, 0.1, 10)):
+        model = syn.graphene_monolayer(shape, onsite=v)
+        kpm = pb.kpm(model, kernel=pb.lorentz_kernel(), silent=True, device=parallel.device_for())
+        return kpm.deferred_ldos(energy, broadening=0.15, position=[0, 0], sublattice="B")
+
+    labels = dict(title="test sweep", x="V (eV)", y="E (eV)", data="LDOS")
+    result = parallel.sweep(factory, labels=labels)
+    assert np.allclose(result.x, golden["sweep.x"]) and np.allclose(result.y, golden["sweep.y"])
+    assert np.allclose(result.data, golden["sweep.data"], rtol=1e-3, atol=1e-6)
+
+    @parallel.parallelize(v1=np.linspace(0, 0.1, 5), v2=np.linspace(-0.2, 0.2, 4))
+    def factory2(v1, v2, energy=np.linspace(0, 0.1, 10)):
+        # pb.constant_potential(v1) then pb.constant_potential(v2): two float32 additions to the onsite energy
+        model = syn.graphene_monolayer(shape, onsite=float(np.float32(v1) + np.float32(v2)))
+        kpm = pb.kpm(model, kernel=pb.lorentz_kernel(), silent=True, device=parallel.device_for())
+        return kpm.deferred_ldos(energy, broadening=0.15, position=[0, 0])
+
+    nd = parallel.ndsweep(factory2)
+    assert nd.data.shape == golden["ndsweep.data"].shape
+    assert np.allclose(nd.data, golden["ndsweep.data"], rtol=1e-3, atol=1e-6)

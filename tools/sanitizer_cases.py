@@ -1,13 +1,14 @@
 #!/usr/bin/env python
-"""Small cases that touch every kernel added late in round 1 (two-step kernel, graph replay, light-cone LDOS, Green's):
-run under compute-sanitizer (memcheck / racecheck / synccheck) by tools/gpu_call15.sh."""
+"""Small cases that touch every kernel of the library (general / staged step kernels for fixed and generic ELL widths,
+lane-aligned batches, graph replay, light-cone LDOS, Green's, Kubo-Bastin): run under compute-sanitizer
+(memcheck / racecheck / synccheck)."""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import pybinding_b200 as pb
 def run(env, fn):
-    for k in ("PBK_PAIR", "PBK_GRAPH", "PBK_CONE", "PBK_PAIR_MINB"): os.environ.pop(k, None)
+    for k in ("PBK_BULK", "PBK_GRAPH", "PBK_CONE", "PBK_DEVBUILD"): os.environ.pop(k, None)
     os.environ.update(env)
     return fn()
 m32 = pb.graphene_rectangle(12.0, dtype=np.complex64, magnetic_field=300.0)
@@ -15,14 +16,20 @@ m64 = pb.graphene_rectangle(10.0, dtype=np.float64, onsite=0.2)
 cub = pb.cubic_anderson(12, disorder=2.0, dtype=np.float32)
 def dos(model, er, M, R):
     return pb.kpm(model, energy_range=er, silent=True).impl.moments_dos(M, R)
-a = run({"PBK_PAIR": "0", "PBK_GRAPH": "0"}, lambda: dos(m32, (-9, 9), 34, 8))
-b = run({"PBK_PAIR": "1", "PBK_GRAPH": "0"}, lambda: dos(m32, (-9, 9), 34, 8))
-c = run({"PBK_PAIR": "2", "PBK_PAIR_MINB": "2"}, lambda: dos(cub, (-8.2, 8.2), 34, 8))
-d = run({"PBK_PAIR": "1"}, lambda: dos(m64, (-9, 9), 34, 6))
+from pybinding_b200 import synthetic as syn
+nnn = syn.graphene_monolayer(pb.Rectangle(9.0), nearest_neighbors=2, dtype=np.float32)   # ELL width 10: generic-width kernels
+a = run({"PBK_BULK": "0", "PBK_GRAPH": "0"}, lambda: dos(m32, (-9, 9), 34, 8))
+b = run({"PBK_BULK": "4", "PBK_GRAPH": "0"}, lambda: dos(m32, (-9, 9), 34, 8))
+c = run({}, lambda: dos(cub, (-8.2, 8.2), 34, 8))
+d = run({}, lambda: dos(nnn, (-9.2, 9.6), 34, 12))
+# batch caps that are not multiples of the 16-byte lane width (f64: 2 lanes, f32: 4 lanes)
+e = run({}, lambda: pb.kpm(m64, energy_range=(-9, 9), silent=True, max_batch=3).impl.moments_dos(34, 7))
+f = run({}, lambda: pb.kpm(cub, energy_range=(-8.2, 8.2), silent=True, max_batch=5).impl.moments_dos(34, 11))
 g = run({}, lambda: [dos(m64, (-9, 9), 34, 1) for _ in range(2)])
 k = pb.kpm(m64, energy_range=(-9, 9), silent=True)
 fn = m64.system.find_nearest
 l1 = k.impl.moments_ldos(66, [fn([0, 0])])
 l2 = k.impl.moments_ldos(18, [fn([0, 0]), fn([3, 3]), fn([-4, 2])])
 gr = k.impl.moments_greens(34, fn([0, 0]), [fn([1, 1]), fn([2, -2])])
-print("pair diff", float(abs(a - b).max() / abs(a).max()), "ok")
+ku = k.impl.moments_kubo(18, m64.system.x, m64.system.y, 2)
+print("staged vs general diff", float(abs(a - b).max() / abs(a).max()), "ok")

@@ -39,7 +39,7 @@ def main():
         env = dict(kv.split("=") for kv in cfg.split(",") if kv)
         max_batch = int(env.pop("MB", 0))   # pseudo-key: vectors per pass
         for k in ("PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL", "PBK_BULK", "PBK_XS",
-                  "PBK_PAIR", "PBK_PAIR_STAGES", "PBK_PAIR_MINB", "PBK_PAIR_R", "PBK_IDENTITY_ORDER", "PBK_MACRO", "PBK_COARSE"):
+                  "PBK_IDENTITY_ORDER", "PBK_MACRO", "PBK_COARSE", "PBK_DEVBUILD", "PBK_RES"):
             os.environ.pop(k, None)
         os.environ.update(env)
         t0 = time.time()
@@ -49,14 +49,14 @@ def main():
         for _ in range(args.reps + 1):
             mom = kpm.impl.moments_dos(args.moments, R)
             s = kpm.stats
-            steps = s.step_launches + s.pair_launches   # a two-step launch advances the recursion twice
+            steps = s.step_launches
             ms = s.step_ms / steps
             best = ms if best is None else min(best, ms)
         gbs = s.step_bytes / steps / (best * 1e-3) / 1e9
         if ref is None:
             ref = mom
         err = float(np.abs(mom - ref).max() / np.abs(ref).max())
-        print(json.dumps(dict(config=cfg, ms_per_step=round(best, 4), pair_launches=int(s.pair_launches), vectors_per_ms=round(s.batch / best, 2), algorithmic_gbs=round(gbs, 1),
+        print(json.dumps(dict(config=cfg, ms_per_step=round(best, 4), vectors_per_ms=round(s.batch / best, 2), algorithmic_gbs=round(gbs, 1),
                               frac=round(gbs / peak, 4), hamiltonian_s=round(s.hamiltonian_time, 2),
                               starter_ms=round(s.starter_ms, 1), batch=s.batch, rel_diff_vs_first=err,
                               total_s=round(time.time() - t0, 1))), flush=True)
