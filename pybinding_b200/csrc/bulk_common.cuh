@@ -33,6 +33,17 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(src)), "r"(bytes) : "memory");
 }
 
+/// A warp hands a ring stage back to the producer.  The stage was read with ld.shared (generic proxy) and will be
+/// overwritten by cp.async.bulk (async proxy): program order + mbarrier release / acquire do not order accesses of two
+/// different proxies, so every lane issues fence.proxy.async before the warp's arrival.  Without it the refill can overtake
+/// reads that are still in flight -- seen as run-to-run differences of ~1e-6 in the moments of few-lane passes on the
+/// 38 M-site system (profiles/r02_diag_r4c.log; compute-sanitizer racecheck had flagged exactly these pairs in round 1).
+__device__ __forceinline__ void release_stage(uint32_t empty_bar, uint32_t tid) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if ((tid & 31u) == 0) mbar_arrive(empty_bar);
+}
+
 // ---- explicit shared-space loads (32-bit addresses: no generic-address arithmetic in the hot loop) ----
 template<class CH> __device__ __forceinline__ CH lds_chunk(uint32_t addr) {
     static_assert(sizeof(CH) == 16, "16-byte chunks");

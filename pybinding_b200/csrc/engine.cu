@@ -224,8 +224,16 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     step_prefetch_mask = static_cast<int>(env_int("PBK_PFMASK", 0));
     bulk_stages = static_cast<int>(env_int("PBK_BULK", 4));
     bulk_xstage = env_int("PBK_XS", 1) != 0;
+    bulk_release = static_cast<int>(env_int("PBK_RELEASE", 0));
     identity_order = env_int("PBK_IDENTITY_ORDER", 0) != 0;
     coarse_sites = env_int("PBK_COARSE", 16);
+    res_mode = static_cast<int>(env_int("PBK_RES", 1));
+    res_tile = env_int("PBK_RES_TILE", 512);
+    res_row_bytes = static_cast<int>(env_int("PBK_RES_ROW", 64));
+    res_ctas = static_cast<int>(env_int("PBK_RES_CTAS", 3));
+    res_stages = static_cast<int>(env_int("PBK_RES_STAGES", 2));
+    if (res_tile < 64 || res_tile % 64 != 0) res_tile = 512;
+    if (res_row_bytes < 16 || res_row_bytes % 16 != 0) res_row_bytes = 64;
     dev_build = static_cast<int>(env_int("PBK_DEVBUILD", 1));
     bcast_order = static_cast<int>(env_int("PBK_BCAST_ORDER", 1));
     macro_tiles = env_int("PBK_MACRO", 256);   // 65 k-site macro-blocks: +4 % on configs[1] in short runs, +1.5 % in the power-capped bench (profiles/r01_ab_order_v6.log)
@@ -258,6 +266,26 @@ void Engine::require_hamiltonian() const {
     if (!has_h) throw Error(PBK_LOGIC_ERROR, "pbkpm: no Hamiltonian has been set");
 }
 
+/// Share of outside rows referenced by a breadth-first ball of `tile` sites grown in the middle of the system: the
+/// halo of a locality cluster relative to its size (0.2 - 0.3 for a 2-D lattice at 256 sites, ~0.9 for a cubic one)
+static double probe_halo_fraction(int64_t n, const int32_t* indptr, const int32_t* indices, int64_t tile) {
+    if (n < 4 * tile) return 0.0;
+    std::vector<int32_t> queue;
+    std::map<int32_t, int> seen;   // site -> 0: inside the ball, 1: halo
+    int32_t const seed = static_cast<int32_t>(n / 2);
+    queue.push_back(seed); seen[seed] = 0;
+    for (size_t head = 0; head < queue.size() && static_cast<int64_t>(queue.size()) < tile; ++head) {
+        int32_t const row = queue[head];
+        for (int p = indptr[row]; p < indptr[row + 1] && static_cast<int64_t>(queue.size()) < tile; ++p) {
+            int32_t const c = indices[p];
+            if (seen.find(c) == seen.end()) { seen[c] = 0; queue.push_back(c); }
+        }
+    }
+    int64_t halo = 0;
+    for (int32_t row : queue) for (int p = indptr[row]; p < indptr[row + 1]; ++p) if (seen.find(indices[p]) == seen.end()) { seen[indices[p]] = 1; ++halo; }
+    return static_cast<double>(halo) / static_cast<double>(queue.size());
+}
+
 void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const int32_t* indices, const void* data) {
     if (dt < 0 || dt > 3) throw Error(PBK_INVALID_ARGUMENT, "invalid dtype");
     if (n_ <= 0 || !indptr || !indices || !data) throw Error(PBK_INVALID_ARGUMENT, "invalid Hamiltonian arrays");
@@ -284,12 +312,18 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
     // attached the Hamiltonian is the same on every rank (the sharding contract), so rank 0 alone computes the
     // ordering and the others receive it by one broadcast over NVLink: set_hamiltonian is then a collective call.
     cluster_tile = 0; cluster_on_device = false; cluster_on_host = false;
+    // cluster size of the layout: 256-row clusters for the staged kernel; where such a cluster is mostly surface (3-D
+    // lattices) larger ones whose x rows the resident-tile kernel keeps in shared memory
+    layout_res = locality_tile > 0 && !identity_order && bulk_stages >= 2 && dev_build &&
+                 (res_mode >= 2 || (res_mode == 1 && n_ >= 64 * res_tile && probe_halo_fraction(n_, indptr, indices, locality_tile) > 0.5));
+    layout_tile = layout_res ? res_tile : locality_tile;
+    int64_t const layout_macro = layout_tile > 0 ? std::max<int64_t>(1, macro_tiles * locality_tile / layout_tile) : macro_tiles;
     bool const want_order = locality_tile > 0 && !identity_order;
     bool const receive_order = want_order && world > 1 && comm && bcast_order && nccl && nccl->Broadcast;
     std::unique_ptr<ScopedThread> ordering;   // joined on every exit path, exceptions of its body re-thrown after the join
     if (want_order && !(receive_order && rank != 0)) {
-        cluster_tile = locality_tile;
-        ordering = std::make_unique<ScopedThread>([this, n_, indptr, indices] { cluster_order(n_, indptr, indices, cluster_tile, cluster_queue, cluster_rmap, macro_tiles, coarse_sites); });
+        cluster_tile = layout_tile;
+        ordering = std::make_unique<ScopedThread>([this, n_, indptr, indices, layout_macro] { cluster_order(n_, indptr, indices, cluster_tile, cluster_queue, cluster_rmap, layout_macro, coarse_sites); });
     }
     size_t const sz = dtype_size(dt);
     h_indptr.resize_uninit(static_cast<size_t>(n) + 1, true);
@@ -311,7 +345,7 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
     if (want_order && dev_build) {   // the ordering on the device: uploaded by its owner, broadcast to the other ranks
         cluster_queue_dev.ensure(sizeof(int32_t) * static_cast<size_t>(n));
         if (cluster_on_host) PBK_CUDA(cudaMemcpyAsync(cluster_queue_dev.as(), cluster_queue.data(), sizeof(int32_t) * static_cast<size_t>(n), cudaMemcpyHostToDevice, stream));
-        if (receive_order) { broadcast(cluster_queue_dev.as(), n, 0); cluster_tile = locality_tile; }
+        if (receive_order) { broadcast(cluster_queue_dev.as(), n, 0); cluster_tile = layout_tile; }
         cluster_on_device = true;
     }
     PBK_CUDA(cudaStreamSynchronize(stream));
@@ -733,6 +767,68 @@ bool Engine::build_layout_on_device(DeviceHamiltonian& dh, int mode, Scale s, co
     return true;
 }
 
+/// Tiles, halo lists and local codes of the resident-tile step kernel for passes of R vectors (kernels_res.cu).  The
+/// nominal tiles are the locality clusters; a tile whose own + halo rows exceed the shared-memory capacity is halved
+/// (a few passes of the counting kernel), then one kernel writes the sorted halo lists and the 16-bit codes.
+bool Engine::ensure_res_meta(DeviceHamiltonian& dh, int R) {
+    if (!dh.res_enabled || !dh.valid) return false;
+    ResGeometry const geo = res_geometry(dtype, dh.ell.k, R, res_ctas, res_stages);
+    if (dh.res_ntiles > 0 && dh.res_geo.row_bytes == geo.row_bytes) return true;
+    if (dh.res_failed_row_bytes == geo.row_bytes) return false;
+    auto fail = [&]() { dh.res_failed_row_bytes = geo.row_bytes; dh.res_ntiles = 0; return false; };
+    int const rpb = geo.rows_per_iteration;
+    if (rpb < 1 || geo.cap_rows < 2 * rpb || dh.tile % rpb != 0 || dh.ell.k > 64) return fail();
+    double const t0 = now_seconds();
+    std::vector<ResTile> tiles;
+    for (int64_t r0 = 0; r0 < n; r0 += dh.tile) tiles.push_back(ResTile{static_cast<int32_t>(r0), static_cast<int32_t>(std::min<int64_t>(dh.tile, n - r0)), 0, 0});
+    std::vector<int32_t> nh;
+    DevBuf tiles_dev, nh_dev;
+    for (int pass = 0; pass < 8; ++pass) {
+        tiles_dev.ensure(sizeof(ResTile) * tiles.size());
+        nh_dev.ensure(sizeof(int32_t) * tiles.size());
+        nh.resize(tiles.size());
+        PBK_CUDA(cudaMemcpyAsync(tiles_dev.as(), tiles.data(), sizeof(ResTile) * tiles.size(), cudaMemcpyHostToDevice, stream));
+        PBK_CUDA(launch_res_count(dh.ell, tiles_dev.as<ResTile>(), static_cast<int>(tiles.size()), nh_dev.as<int32_t>(), stream));
+        PBK_CUDA(cudaMemcpyAsync(nh.data(), nh_dev.as(), sizeof(int32_t) * tiles.size(), cudaMemcpyDeviceToHost, stream));
+        PBK_CUDA(cudaStreamSynchronize(stream));
+        ++launches;
+        std::vector<ResTile> next;
+        next.reserve(tiles.size() + tiles.size() / 4);
+        bool split = false;
+        for (size_t t = 0; t < tiles.size(); ++t) {
+            ResTile tl = tiles[t];
+            tl.nh = nh[t];
+            if (tl.nrows + tl.nh <= geo.cap_rows && tl.nh <= res_max_halo()) { next.push_back(tl); continue; }
+            if (tl.nrows < 2 * rpb) return fail();       // even the smallest tile does not fit
+            int32_t const first = (tl.nrows / 2 + rpb - 1) / rpb * rpb;
+            next.push_back(ResTile{tl.row0, first, 0, -1});
+            next.push_back(ResTile{tl.row0 + first, tl.nrows - first, 0, -1});
+            split = true;
+        }
+        tiles.swap(next);
+        if (!split) break;
+        if (pass == 7) return fail();
+    }
+    int64_t halo_total = 0;
+    for (auto& tl : tiles) { tl.halo_off = static_cast<int32_t>(halo_total); halo_total += tl.nh; }
+    if (halo_total >= (int64_t{1} << 31)) return fail();
+    dh.res_tiles.ensure(sizeof(ResTile) * tiles.size());
+    dh.res_halo.ensure(sizeof(int32_t) * static_cast<size_t>(std::max<int64_t>(halo_total, 1)));
+    dh.res_codes.ensure(static_cast<size_t>(n) * geo.cb);
+    dh.res_vals.ensure(static_cast<size_t>(n) * geo.kvb);
+    PBK_CUDA(cudaMemcpyAsync(dh.res_tiles.as(), tiles.data(), sizeof(ResTile) * tiles.size(), cudaMemcpyHostToDevice, stream));
+    PBK_CUDA(launch_res_fill(dtype, dh.ell, dh.res_tiles.as<ResTile>(), static_cast<int>(tiles.size()), dh.res_halo.as<int32_t>(),
+                             dh.res_codes.as(), dh.res_vals.as(), geo, stream));
+    PBK_CUDA(cudaStreamSynchronize(stream));
+    ++launches;
+    dh.res_ntiles = static_cast<int>(tiles.size());
+    dh.res_geo = geo;
+    dh.res_halo_frac = static_cast<double>(halo_total) / static_cast<double>(n);
+    if (std::getenv("PBK_TIMING")) std::fprintf(stderr, "[pbkpm] resident-tile metadata: %zu tiles (nominal %lld rows, capacity %d rows of %u bytes), halo %.2f x rows, %.3f s\n",
+                                                 tiles.size(), static_cast<long long>(dh.tile), geo.cap_rows, geo.row_bytes, dh.res_halo_frac, now_seconds() - t0);
+    return true;
+}
+
 /// host copies of a layout's order maps: they exist already when the host computed the order, and are downloaded on
 /// first use when the order arrived by broadcast (only index look-ups and host-built operators need them)
 void Engine::ensure_host_order(DeviceHamiltonian& dh) {
@@ -776,19 +872,21 @@ void Engine::build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int or
             queue.resize(n);
             for (int64_t i = 0; i < n; ++i) queue[i] = static_cast<int32_t>(i);
             dh.reorder_map = queue;
-        } else if (cluster_tile == locality_tile && (cluster_on_host || cluster_on_device)) {   // computed / received by set_hamiltonian
+        } else if (cluster_tile == layout_tile && (cluster_on_host || cluster_on_device)) {   // computed / received by set_hamiltonian
             if (cluster_on_host) { queue.swap(cluster_queue); dh.reorder_map.swap(cluster_rmap); }
             else dh.host_order = false;
             if (cluster_on_device) { dh.queue_dev = std::move(cluster_queue_dev); order_on_device = true; }
             cluster_tile = 0; cluster_on_host = cluster_on_device = false;
         } else {
-            cluster_order(n, h_indptr.data(), h_indices.data(), locality_tile, queue, dh.reorder_map, macro_tiles, coarse_sites);
+            cluster_order(n, h_indptr.data(), h_indices.data(), layout_tile, queue, dh.reorder_map,
+                          std::max<int64_t>(1, macro_tiles * locality_tile / layout_tile), coarse_sites);
         }
         dh.idx = target;   // positions in this layout are looked up where they are needed (ensure_host_order)
         if (dh.host_order) { dh.idx = Indices{}; for (int32_t i : target.src) dh.idx.src.push_back(dh.reorder_map[i]); for (int32_t i : target.dest) dh.idx.dest.push_back(dh.reorder_map[i]); }
         dh.map.data = {static_cast<int32_t>(n)};
         dh.reordered = true;
-        dh.tile = locality_tile;
+        dh.tile = identity_order ? locality_tile : layout_tile;
+        dh.res_enabled = layout_res && !identity_order;
     } else if (order == ORDER_BFS) {
         if (bfs_ready.valid_for(target)) {  // moments_ldos already ran the relabelling to look at the slice map
             queue = std::move(bfs_ready.queue);
@@ -1117,6 +1215,9 @@ int Engine::pick_batch(int vectors, int extra_blocks) const {
     int const hard = 4096 / dtype_size(dtype);  // 256 chunks of 16 bytes per row
     cap = std::min(cap, hard);
     cap = std::min(cap, config.max_batch > 0 ? config.max_batch : 64);
+    // layouts ordered for the resident-tile kernel advance as many vectors per pass as its row width holds
+    if (natural.valid && natural.res_enabled && natural.res_failed_row_bytes != static_cast<uint32_t>(res_row_bytes))
+        cap = std::min(cap, std::max(1, res_row_bytes / dtype_size(dtype)));
     if (cap < 1) throw Error(PBK_RUNTIME_ERROR, "pbkpm: not enough device memory for one KPM vector pair");
     // a pass of more than one vector is padded to whole 16-byte chunks (lane_pad), so the batch itself must be a
     // multiple of the chunk width: buffers are sized for `rb` lanes and every launch uses lane_pad(lanes) <= rb
@@ -1143,12 +1244,22 @@ void Engine::step(DeviceHamiltonian const& h, const void* x, void* y, void* y2, 
     a.partials = partials.as<double>(); a.counter = counter.as<unsigned>(); a.mom = mom.as<double>(); a.m01 = m01.as<double>();
     a.M = M; a.n = nstep; a.fin = fin;
     a.tile = h.tile; a.tpb = step_tpb; a.blocks_per_sm = step_blocks_per_sm; a.prefetch = step_prefetch; a.prefetch_mask = step_prefetch_mask;
-    a.packed = h.packed.bytes() ? h.packed.as() : nullptr; a.bulk_stages = bulk_stages; a.bulk_xstage = bulk_xstage;
+    a.packed = h.packed.bytes() ? h.packed.as() : nullptr; a.bulk_stages = bulk_stages; a.bulk_xstage = bulk_xstage; a.bulk_release = bulk_release;
     LaunchInfo info;
-    PBK_CUDA(launch_step(dtype, a, num_sms, stream, &info));
+    bool done = false;
+    if (h.res_enabled && subtract && sums && !y2 && nrows == n && &h == &natural && ensure_res_meta(natural, R)) {
+        ResArgs r;
+        r.tiles = h.res_tiles.as<ResTile>(); r.ntiles = h.res_ntiles; r.halo_rows = h.res_halo.as<int32_t>();
+        r.codes = h.res_codes.as(); r.vals = h.res_vals.as(); r.geo = h.res_geo;
+        r.x = x; r.y = y; r.nrows = nrows; r.R = R; r.k = h.ell.k;
+        r.partials = a.partials; r.counter = a.counter; r.mom = a.mom; r.m01 = a.m01; r.M = M; r.n = nstep; r.fin = fin;
+        PBK_CUDA(launch_step_res(dtype, r, num_sms, stream, &info, &done));
+    }
+    if (!done) PBK_CUDA(launch_step(dtype, a, num_sms, stream, &info));
     ++launches;
     ++stats.step_launches;
-    if (info.bulk) ++stats.bulk_launches;
+    if (info.res) ++stats.res_launches;
+    else if (info.bulk) ++stats.bulk_launches;
     int const s = dtype_size(dtype);
     stats.step_bytes += static_cast<double>(nrows) * (h.ell.k * (s + 4.0) + static_cast<double>(R) * s * (2 + (subtract ? 1 : 0) + (y2 ? 1 : 0)));
 }
@@ -1174,7 +1285,8 @@ void Engine::run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_siz
     };
     // Small systems are launch-bound (a step is a few microseconds of work): capture the whole sequence once as a
     // CUDA graph and replay it on later runs with the same buffers and row counts.
-    bool const graphable = graph_mode && !h.transient && M / 2 >= 8 &&
+    if (h.res_enabled && &h == &natural && !opt_size) ensure_res_meta(natural, R);   // before any capture: it synchronises
+    bool const graphable = graph_mode && !h.transient && !h.res_enabled && M / 2 >= 8 &&
                            static_cast<double>(nv) * R * dtype_size(dtype) <= graph_max_bytes;
     bool done = false;
     if (graphable) {
@@ -1182,7 +1294,7 @@ void Engine::run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_siz
                                     reinterpret_cast<int64_t>(r0), reinterpret_cast<int64_t>(r1), reinterpret_cast<int64_t>(mom.as()),
                                     reinterpret_cast<int64_t>(partials.as()), reinterpret_cast<int64_t>(m01.as()), reinterpret_cast<int64_t>(counter.as()),
                                     h.ell.pitch, h.ell.k, h.tile, R, M, opt_size ? 1 : 0, nv, dtype, step_tpb, step_blocks_per_sm, step_prefetch,
-                                    bulk_stages, bulk_xstage ? 1 : 0};
+                                    bulk_stages, bulk_xstage ? 1 : 0, h.res_enabled ? 1 : 0, reinterpret_cast<int64_t>(h.res_tiles.as())};
         if (opt_size) for (int k = 1; k <= M / 2; ++k) key.push_back(h.map.optimal_size(k, M));
         auto it = graph_cache.find(key);
         if (it == graph_cache.end()) {

@@ -129,6 +129,13 @@ struct DeviceHamiltonian {
     DevBuf val, col, perm;
     DevBuf queue_dev;              // row of the layout -> original site, on the device (layouts built by build.cu)
     bool host_order = true;        // reorder_map / order_queue hold the host copies of perm / queue_dev (else: downloaded on first use)
+    // resident-tile variant of the step kernel (kernels_res.cu): chosen for layouts whose clusters are mostly surface
+    bool res_enabled = false;      // the layout was ordered for it (tile = rows of a nominal resident tile)
+    DevBuf res_tiles, res_halo, res_codes, res_vals;
+    int res_ntiles = 0;
+    uint32_t res_failed_row_bytes = 0;   // a row width for which the tiles did not fit (not retried)
+    ResGeometry res_geo;
+    double res_halo_frac = 0;      // halo rows / own rows over all tiles
     DevBuf packed;                 // row-major packed copy of the ELL arrays for the bulk-copy staged step kernel (ORDER_CLUSTER only)
     EllDev ell;
     double seconds = 0;
@@ -233,8 +240,15 @@ private:
     int device = 0;
     int num_sms = 148;
     int step_tpb = 256, step_blocks_per_sm = 0, step_prefetch = 0, step_prefetch_mask = 0;
+    int res_mode = 1;            // PBK_RES: resident-tile step kernel -- 0 off, 1 where the locality clusters are mostly surface, 2 always
+    int64_t res_tile = 512;      // PBK_RES_TILE: rows of a nominal resident tile (the locality clusters of such layouts)
+    int res_row_bytes = 64;      // PBK_RES_ROW: bytes per row of a pass of the resident kernel (16 float lanes)
+    int res_ctas = 3, res_stages = 2;   // PBK_RES_CTAS, PBK_RES_STAGES
+    int64_t layout_tile = 0;     // cluster size of the current Hamiltonian's full-system layout
+    bool layout_res = false;     // ... and whether it was ordered for the resident kernel
     int bulk_stages = 4;         // pipeline depth of the bulk-copy staged step kernel (0: general kernel only)
     bool bulk_xstage = true;     // staged kernel: the CTA's own x rows go through shared memory too
+    int bulk_release = 0;        // PBK_RELEASE (experiment): when a warp hands a stage back to the producer
     int64_t locality_tile = 0;   // rows per locality cluster of the full-system layout (0: keep the caller's order)
     pbk_config config{};
     cudaStream_t stream = nullptr;
@@ -308,6 +322,7 @@ private:
     void build_device_hamiltonian(DeviceHamiltonian& dh, bool scaled, int order, Indices const& target);
     /// the layout's rows written by build.cu from the resident CSR; false: not applicable (rows too long), use the host path
     bool build_layout_on_device(DeviceHamiltonian& dh, int mode, Scale s, const float* positions_dev);
+    bool ensure_res_meta(DeviceHamiltonian& dh, int R);   // tiles, halo lists and local codes of the resident-tile kernel
     void ensure_host_order(DeviceHamiltonian& dh);   // host copies of a layout's order maps (downloaded on first use)
     void broadcast(void* dev, int64_t count_int32, int root);
     DeviceHamiltonian& natural_hamiltonian();

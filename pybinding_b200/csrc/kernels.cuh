@@ -50,9 +50,10 @@ struct StepArgs {
     const void* packed = nullptr;  // row-major packed copy of h (launch_pack_ell); required by the staged variant
     int bulk_stages = 0;         // >= 2: use the staged variant with this pipeline depth where it applies
     bool bulk_xstage = true;     // stage the CTA's own x rows too (else: L2 bulk prefetch + read through L1)
+    int bulk_release = 0;        // experiment knob: when a warp hands a stage back to the producer (see kernels_bulk.cu)
 };
 
-struct LaunchInfo { int grid = 0, block = 0, V = 0, K = 0, bulk = 0; };
+struct LaunchInfo { int grid = 0, block = 0, V = 0, K = 0, bulk = 0, res = 0; };
 
 /// Fused Chebyshev step (K1/K2/K3).  Returns the launch geometry used (for stats / tests).
 cudaError_t launch_step(int dtype, StepArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info);
@@ -65,6 +66,33 @@ constexpr int PACKED_PAD_ROWS = 256;
 void packed_record_layout(int scalar_bytes, int k, uint32_t* gran, uint32_t* valoff);
 size_t packed_ell_bytes(int dtype, EllDev const& h);
 cudaError_t launch_pack_ell(int dtype, EllDev const& h, void* packed, cudaStream_t s);
+// ---- resident-tile variant (kernels_res.cu): the x rows of a tile and of its halo live in shared memory ----
+struct ResTile { int32_t row0, nrows, halo_off, nh; };   // rows [row0, row0 + nrows); halo_rows[halo_off .. + nh)
+struct ResGeometry {
+    uint32_t row_bytes = 0;        // bytes of one row of a vector block (lanes * sizeof scalar): the variant is built for one width
+    uint32_t cb = 0, kvb = 0;      // bytes per row of the code records (uint16, padded to 16) and of the value records (padded to 16)
+    uint32_t xs_bytes = 0;         // shared memory of the resident tile
+    int cap_rows = 0;              // own + halo rows that fit
+    int stages = 2, ctas_per_sm = 3, rows_per_iteration = 0;
+};
+ResGeometry res_geometry(int dtype, int k, int lanes, int ctas_per_sm, int stages);
+int res_max_halo();
+/// nh_dev[t] = distinct rows outside tile t referenced by its rows (> res_max_halo(): too many to tell)
+cudaError_t launch_res_count(EllDev const& h, const ResTile* tiles_dev, int ntiles, int32_t* nh_dev, cudaStream_t s);
+/// halo lists (ascending) + per-row 16-bit local codes and values, for tiles whose halo_off / nh are final
+cudaError_t launch_res_fill(int dtype, EllDev const& h, const ResTile* tiles_dev, int ntiles, int32_t* halo_rows, void* codes, void* vals,
+                            ResGeometry const& g, cudaStream_t s);
+struct ResArgs {
+    const ResTile* tiles = nullptr; int ntiles = 0;
+    const int32_t* halo_rows = nullptr; const void* codes = nullptr; const void* vals = nullptr;
+    ResGeometry geo;
+    const void* x = nullptr; void* y = nullptr;
+    int64_t nrows = 0; int R = 1, k = 0;
+    double* partials = nullptr; unsigned* counter = nullptr; double* mom = nullptr; double* m01 = nullptr; int M = 0, n = 0, fin = FIN_NONE;
+};
+/// y = H x - y with the fused sums (the step of the diagonal recursion); *handled == false: not applicable
+cudaError_t launch_step_res(int dtype, ResArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info, bool* handled);
+
 /// Upper bound of blocks launch_step may use (size of the partials buffer = this * R * 3 doubles)
 int max_step_blocks(int num_sms);
 

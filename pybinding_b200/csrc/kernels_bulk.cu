@@ -35,6 +35,7 @@ struct BulkDev {  // kernel parameters
     const void* x; void* y;
     int nrows, cpr, rpb, ipt, tile_jump;  // tile_jump: rows to skip to reach this CTA's next tile
     int R, stages, k;
+    int release;                          // when a warp hands a stage back: 0 right after reading it, 1 after the row is finished
     uint32_t gran, valoff, stage_bytes;   // valoff = 16 K: offset of the values inside a granule
     double* partials; unsigned* counter; double* mom; double* m01; int M; int n; int fin;
 };
@@ -131,8 +132,7 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_bulk(BulkDev a) {
 #pragma unroll
                 for (int s = 0; s < K; ++s) { c[s] = lds_i32(sb + my_rec + 4u * s); lds_val(sb + my_val + static_cast<uint32_t>(sizeof(T)) * s, v[s]); }
             }
-            __syncwarp();
-            if ((tid & 31u) == 0) mbar_arrive(fb + empty_off);  // this warp is done with the stage
+            if (a.release == 0) release_stage(fb + empty_off, tid);   // this warp is done with the stage
 
             if (valid) {
                 CH xg[K];
@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_bulk(BulkDev a) {
                 }
                 store_cs(y + ci, out);
             }
+            if (a.release != 0) release_stage(fb + empty_off, tid);   // experiment: hand the stage back only after the row is finished
         } else {
             CH out;
             if (valid) {
@@ -173,8 +174,7 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_bulk(BulkDev a) {
                     }
                 }
             }
-            __syncwarp();
-            if ((tid & 31u) == 0) mbar_arrive(fb + empty_off);  // the records were read slot by slot: release the stage now
+            release_stage(fb + empty_off, tid);  // the records were read slot by slot: release the stage now
             if (valid) {
 #pragma unroll
                 for (int e = 0; e < V; ++e) sums_(acc + e * C, xr.e[e], out.e[e]);
@@ -288,7 +288,7 @@ cudaError_t launch_bulk_t(StepArgs const& a, int num_sms, cudaStream_t stream, L
     d.x = a.x; d.y = a.y;
     d.nrows = static_cast<int>(a.nrows); d.cpr = cpr; d.rpb = rpb; d.ipt = ipt;
     d.tile_jump = static_cast<int>((grid - 1) * tile_rows);
-    d.R = a.R; d.stages = stages; d.k = a.h.k; d.gran = gran; d.valoff = valoff; d.stage_bytes = stage_bytes;
+    d.R = a.R; d.stages = stages; d.k = a.h.k; d.release = a.bulk_release; d.gran = gran; d.valoff = valoff; d.stage_bytes = stage_bytes;
     d.partials = a.partials; d.counter = a.counter; d.mom = a.mom; d.m01 = a.m01; d.M = a.M; d.n = a.n; d.fin = a.fin;
     fn<<<grid, BULK_TPB, dyn, stream>>>(d);
     *handled = true;

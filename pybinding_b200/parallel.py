@@ -13,6 +13,7 @@ host-bound and spread over several GPUs when `devices` names more than one (`dev
 device job `idx` should build its solver on).  ctypes / pybind11 release the GIL during every engine call, like
 `wrappers.hpp:15` does for the reference.
 """
+import inspect
 import itertools
 import queue
 import threading
@@ -145,22 +146,25 @@ class NDSweep:
 
 
 class _Factory:
-    def __init__(self, variables, produce, num_threads, queue_size, devices):
+    def __init__(self, variables, produce, num_threads, queue_size, devices, fixtures=None):
         self.variables = [np.atleast_1d(v) for v in variables]
         self.sequence = list(itertools.product(*self.variables))
         self.produce = produce
+        self.fixtures = dict(fixtures or {})   # keyword defaults of the factory function, e.g. `energy` (parallel.py:352-353)
         self.num_threads, self.queue_size, self.devices = num_threads, queue_size, devices
 
 
 def parallelize(num_threads=4, queue_size=None, devices=None, **variables):
     """Decorator: `@parallelize(a=values_a, b=values_b) def factory(a, b): return kpm.deferred_ldos(...)`
     (reference: pybinding/parallel.py:314-360); the product of the keyword sequences is the sweep."""
-    names = list(variables)
-
     def decorator(produce_func):
+        params = inspect.signature(produce_func).parameters
+        names = [k for k in params if k in variables]          # the order of the function's parameters, like the reference
+        fixtures = {k: v.default for k, v in params.items() if k not in variables and v.default is not inspect.Parameter.empty}
+
         def produce(values):
             return produce_func(**dict(zip(names, values)))
-        return _Factory([variables[n] for n in names], produce, num_threads, queue_size, devices)
+        return _Factory([variables[n] for n in names], produce, num_threads, queue_size, devices, fixtures)
     return decorator
 
 
@@ -183,7 +187,10 @@ def sweep(factory, labels=None, tags=None):
 
     def make_result(data):
         first = data[0]
-        y = getattr(first, "variable", np.arange(np.size(getattr(first, "data", first))))
+        if "energy" in factory.fixtures:      # the reference's convention: y is the factory's `energy` default (parallel.py:378-384)
+            y = np.asarray(factory.fixtures["energy"])
+        else:
+            y = getattr(first, "variable", np.arange(np.size(getattr(first, "data", first))))
         rows = [np.asarray(getattr(d, "data", d)).squeeze() for d in data]
         return Sweep(x, y, np.vstack(rows), labels, tags)
 
@@ -191,11 +198,17 @@ def sweep(factory, labels=None, tags=None):
 
 
 def ndsweep(factory, labels=None, tags=None):
-    """N-variable sweep: data has the shape of the variable grid (+ the shape of one result)
-    (reference: pybinding/parallel.py:396-430)"""
+    """N-variable sweep: `NDSweep(variables + (energy,), data)` with `data.shape == [len(v) for v in variables]`
+    (reference: pybinding/parallel.py:396-430, results.py:1027-1050).  Without an `energy` fixture the trailing axes are
+    the shape of one result."""
     def make_result(data):
-        arrays = [np.asarray(getattr(d, "data", d)) for d in data]
-        shape = tuple(len(v) for v in factory.variables) + arrays[0].shape
-        return NDSweep(factory.variables, np.reshape(np.stack(arrays), shape), labels, tags)
+        arrays = [np.asarray(getattr(d, "data", d)).squeeze() for d in data]
+        if "energy" in factory.fixtures:
+            variables = list(factory.variables) + [np.asarray(factory.fixtures["energy"])]
+            shape = tuple(len(v) for v in variables)
+        else:
+            variables = list(factory.variables)
+            shape = tuple(len(v) for v in variables) + arrays[0].shape
+        return NDSweep(variables, np.reshape(np.vstack([a.ravel() for a in arrays]), shape), labels, tags)
 
     return parallel_for(factory, make_result)

@@ -23,7 +23,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.complex64): 1e-5,
        np.dtype(np.float64): 1e-11, np.dtype(np.complex128): 1e-11}
-KNOBS = ("PBK_DEVBUILD", "PBK_BULK", "PBK_XS", "PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL",
+KNOBS = ("PBK_RES", "PBK_RES_TILE", "PBK_RES_ROW", "PBK_RES_CTAS", "PBK_RES_STAGES", "PBK_RELEASE", "PBK_DEVBUILD", "PBK_BULK", "PBK_XS", "PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL",
          "PBK_CONE",
          "PBK_GRAPH", "PBK_GRAPH_MAX_MB")
 
@@ -271,3 +271,35 @@ def test_layouts_built_on_the_device_equal_the_host_build(dtype):
                                 kubo=kpm.impl.moments_kubo(18, model.system.x, model.system.y, 1)))
     for key in results[0]:
         assert np.array_equal(np.asarray(results[0][key]), np.asarray(results[1][key])), key
+
+
+@pytest.mark.parametrize("k", [3, 4, 7, 10])
+@pytest.mark.parametrize("dtype", [np.float32, np.complex64, np.float64, np.complex128], ids=lambda d: np.dtype(d).name)
+def test_resident_tile_kernel_matches_general_kernel_and_oracle(dtype, k):
+    """`cheb_step_res` (kernels_res.cu: x rows of a tile and its halo resident in shared memory, 16-bit local codes)
+    against the general kernel and the oracle: every dtype, the specialised widths and a generic one, tiles that have
+    to be split because their halo does not fit, several row widths / pipeline depths / CTAs per SM"""
+    dtype = np.dtype(dtype)
+    if k == 10:
+        from pybinding_b200 import synthetic as syn
+        model = syn.graphene_monolayer(pb.Rectangle(9.0), nearest_neighbors=2, dtype=dtype, magnetic_field=300.0 if dtype.kind == "c" else 0.0)
+        er = (-9.6, 9.6)
+    else:
+        model, er = model_for(dtype, k)
+    M = 66
+    lanes = 64 // dtype.itemsize                     # one pass of the default 64-byte rows
+    R = 2 * lanes + 1                                # two full passes and a ragged one
+    general, s0 = dos_moments(model, er, M, R, PBK_BULK=0, PBK_RES=0)
+    assert s0.res_launches == 0
+    expected = OracleKPM(model.hamiltonian, energy_range=er, hp=True).dos_moments(M, R)
+    assert rel_err(general, expected) < TOL[dtype]
+    for kw in (dict(PBK_RES_TILE=128), dict(PBK_RES_TILE=64, PBK_RES_STAGES=4, PBK_RES_CTAS=1),
+               dict(PBK_RES_TILE=256, PBK_RES_ROW=128, PBK_RES_CTAS=2), dict(PBK_RES_TILE=1024, PBK_RES_ROW=32, PBK_RES_CTAS=4)):
+        res, s1 = dos_moments(model, er, M, R, PBK_RES=2, **kw)
+        full_passes = sum(1 for b in range(s1.num_batches))   # every pass (also the ragged one, padded to whole chunks) runs resident
+        assert s1.res_launches == (M // 2 - 1) * full_passes, "the resident-tile kernel did not run: {} {}".format(kw, s1.res_launches)
+        assert rel_err(res, expected) < TOL[dtype], kw
+        assert rel_err(res, general) < (1e-12 if dtype.itemsize >= 8 and dtype != np.complex64 else 1e-6), kw
+    again, _ = dos_moments(model, er, M, R, PBK_RES=2, PBK_RES_TILE=128)
+    first, _ = dos_moments(model, er, M, R, PBK_RES=2, PBK_RES_TILE=128)
+    assert np.array_equal(again, first), "moments must be bit-reproducible run to run"
