@@ -41,6 +41,22 @@ WORKLOADS = {
                                    moments=514, vectors=64, energy_range=(-8.5, 8.5),
                                    text="(reduced, for quick checks) graphene 200x200 nm calc_dos, 514 moments, 64 vectors"),
 }
+# BASELINE configs[2] and configs[3]: not the headline metric, each prints its own line (own metric name, own roofline)
+QUANTITY_WORKLOADS = {
+    "graphene_500nm_c128_ldos": dict(kind="graphene", size=500.0, field=10.0, disorder=0.5, dtype="complex128", quantity="ldos",
+                                     sites=256, broadening=0.02, energy_range=(-8.8, 8.8),
+                                     text="graphene 500x500 nm + onsite disorder + Peierls field, complex128, calc_ldos at 256 sites "
+                                          "(16 x 16 grid), broadening 0.02 eV"),
+    "graphene_500nm_c128_greens": dict(kind="graphene", size=500.0, field=10.0, disorder=0.5, dtype="complex128", quantity="greens",
+                                       sites=256, broadening=0.02, energy_range=(-8.8, 8.8),
+                                       text="graphene 500x500 nm + onsite disorder + Peierls field, complex128, calc_greens centre -> "
+                                            "256 sites within 40 nm, broadening 0.02 eV"),
+    "graphene_200nm_f64_conductivity": dict(kind="graphene", size=200.0, field=0.0, disorder=0.0, dtype="float64", quantity="conductivity",
+                                            vectors=4, points=1000, energy_range=(-9.0, 9.0),
+                                            text="graphene 200x200 nm calc_conductivity xx and xy, 514 x 514 Kubo-Bastin moments, "
+                                                 "4 random vectors, float64, 1000 points, T = 300 K"),
+}
+FP64_TENSOR_PEAK = 37.1   # TFLOP/s, DMMA.8x8x4 measured on this pool's B200 (profiles/r01_fp64_mma_probe.jsonl); not in MEASURED_PEAKS.json
 DEFAULT_WORKLOAD = "graphene_1000nm_c64_dos"
 METRIC = "KPM nnz*moments*vectors/s (graphene DOS)"
 UNIT = "nnz*moments*vectors/s"
@@ -49,7 +65,8 @@ UNIT = "nnz*moments*vectors/s"
 def build_model(w):
     import pybinding_b200 as pb
     if w["kind"] == "graphene":
-        return pb.graphene_rectangle(w["size"], magnetic_field=w["field"], dtype=np.dtype(w["dtype"]))
+        return pb.graphene_rectangle(w["size"], magnetic_field=w["field"], dtype=np.dtype(w["dtype"]),
+                                     disorder=w.get("disorder", 0.0), disorder_seed=0)
     return pb.cubic_anderson(w["size"], disorder=4.0, seed=0, dtype=np.dtype(w["dtype"]))
 
 
@@ -236,6 +253,109 @@ def run_reference(args, w):
     emit(out)
 
 
+def run_quantity(args, name, w):
+    """configs[2] / configs[3] through the public API: one step = one API call with host buffers in and curves out.
+    Parity first (a bounded piece of the same calculation against the hp oracle), then W warm-up and K timed calls."""
+    import pybinding_b200 as pb
+    from oracle.oracle import OracleKPM, hardware_threads
+    rank = int(os.environ.get("RANK", "0"))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and rank != 0:
+        return   # single-GPU lines
+    model = build_model(w)
+    n, nnz = model.hamiltonian.shape[0], model.hamiltonian.nnz
+    tol = TOLERANCE[w["dtype"]]
+    sampler = ClockSampler(0)
+    q = w["quantity"]
+    if q in ("ldos", "greens"):
+        kpm = pb.kpm(model, energy_range=w["energy_range"], silent=True)
+        ref = OracleKPM(model.hamiltonian, energy_range=w["energy_range"], hp=True)
+        g = int(round(np.sqrt(w["sites"])))
+        energy = np.linspace(-1, 1, 500)
+        M = kpm.kernel.required_num_moments(w["broadening"] / kpm.scaling_factors[0])
+        if q == "ldos":
+            xs = np.linspace(-0.4 * w["size"], 0.4 * w["size"], g)
+            sites = [model.system.find_nearest([x, y]) for x in xs for y in xs][:w["sites"]]
+            err = float(np.abs(kpm.impl.moments_ldos(M, sites[:1]) - ref.ldos_moments(M, sites[:1])).max() / 0.5)
+            call = lambda: kpm.impl._ldos_indices(sites, energy, w["broadening"])
+        else:
+            xs = np.linspace(-20.0, 20.0, g)
+            sites = [model.system.find_nearest([x, y]) for x in xs for y in xs][:w["sites"]]
+            row = model.system.find_nearest([0.0, 0.0])
+            expected = ref.greens_moments(M, row, sites[:4])
+            err = float(np.abs(kpm.impl.moments_greens(M, row, sites[:4]) - expected).max() / np.abs(expected).max())
+            call = lambda: kpm.calc_greens(row, sites, energy, w["broadening"])
+        parity = dict(parity_max_rel=err, tolerance=tol, passed=bool(err <= tol),
+                      what="raw moments ({} moments) of {} against the hp oracle".format(M, "one site" if q == "ldos" else "four destinations"))
+        units = lambda st: 2.0 * st.opt_nnz * st.multiplier if q == "ldos" else float(st.opt_nnz) * len(sites)
+        metric = "KPM nnz*moments*{}/s on light-cone rows (graphene {})".format("sites" if q == "ldos" else "destinations", q.upper())
+    else:
+        kpm = pb.kpm(model, energy_range=w["energy_range"], kernel=pb.lorentz_kernel(), silent=True)
+        ref = OracleKPM(model.hamiltonian, energy_range=w["energy_range"], kernel="lorentz", hp=True, num_threads=hardware_threads())
+        a, _ = kpm.scaling_factors
+        broadening = a * 4.0 / 512.5     # Lorentz lambda = 4 -> 514 moments
+        mu = np.linspace(-1, 1, 101)
+        x, y = model.system.x, model.system.y
+        expected = ref.kubo_moments(66, x, y, 2)
+        err = float(np.abs(kpm.impl.moments_kubo(66, x, y, 2) - expected).max() / np.abs(expected).max())
+        parity = dict(parity_max_rel=err, tolerance=5 * tol, passed=bool(err <= 5 * tol),
+                      what="66 x 66 Kubo-Bastin moment matrix (xy, 2 vectors) against the hp oracle")
+        M = 514
+        gemm = dict(ms=0.0, flops=0.0, step_ms=0.0)
+
+        def call():
+            out = []
+            for direction in ("xx", "xy"):
+                out.append(kpm.calc_conductivity(mu, broadening, 300.0, direction, num_random=w["vectors"], num_points=w["points"]).data)
+                st = kpm.stats
+                assert st.num_moments == M, st.num_moments
+                gemm["ms"] += st.gemm_ms; gemm["flops"] += st.gemm_flops; gemm["step_ms"] += st.step_ms
+            return out
+        units = lambda st: 2.0 * float(nnz) * M * M * w["vectors"] / M   # per direction pair: 2 x M recursion steps over nnz, per vector
+        metric = "KPM Kubo-Bastin sigma_xx + sigma_xy calls/s (graphene 200 nm, 514 moments, 4 vectors)"
+    if not parity["passed"]:
+        sys.stderr.write("bench.py: PARITY FAILED for {}: {}\n".format(name, parity))
+        emit(dict(metric=metric, value=None, error="parity failed", parity=parity))
+        sys.exit(1)
+    for _ in range(max(args.warmup, 1)):
+        call()
+    if q == "conductivity":
+        gemm.update(ms=0.0, flops=0.0, step_ms=0.0)
+    times, dev_ms, launches = [], [], 0
+    sampler.start()
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        out = call()
+        times.append(time.perf_counter() - t0)
+        st = kpm.stats
+        dev_ms.append(st.moments_device_ms)
+        launches += st.kernel_launches
+    clocks = sampler.stop()
+    st = kpm.stats
+    t = float(np.mean(times))
+    peak, peak_src = measured_peak()
+    if q == "conductivity":
+        tf = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] else 0.0
+        roofline = dict(bound="tensor", achieved=tf, peak=FP64_TENSOR_PEAK, unit="TFLOP/s", frac=tf / FP64_TENSOR_PEAK, traffic=None,
+                        peak_source="FP64 DMMA.8x8x4 peak measured with tools/probe/dmma_probe.cu (profiles/r01_fp64_mma_probe.jsonl)",
+                        kernel="kubo_gemm_kernel (mu += L R^H over sites x lanes, mma.sync f64)",
+                        gemm_ms_per_call=gemm["ms"] / args.steps, recursion_ms_per_call=gemm["step_ms"] / args.steps)
+        value, unit = 1.0 / t, "calls/s"
+    else:
+        gbs = st.step_bytes / (st.step_ms * 1e-3) / 1e9 if st.step_ms else 0.0
+        roofline = dict(bound="hbm", achieved=gbs, peak=peak, unit="GB/s", frac=gbs / peak, traffic=None, peak_source=peak_src,
+                        kernel="cone_group_step_kernel / cheb_step on light-cone sub-systems (working sets near the L2 size: "
+                               "reported against HBM for reference, see DESIGN.md)",
+                        removed_by_light_cone=1.0 - st.opt_nnz / max(st.nnz, 1))
+        value, unit = units(st) / t, "nnz*moments*units/s"
+    emit(dict(metric=metric, value=value, unit=unit, n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3,
+              higher_is_better=True, scaling="strong", vs_baseline=None, dtype=w["dtype"], data="synthetic",
+              config=dict(workload=w["text"], sites=int(n), nnz=int(nnz), moments=int(M),
+                          moments_device_ms=float(np.mean(dev_ms)), timing="wall clock around the public API call (host buffers in, curves out)"),
+              roofline=roofline, cpu_baseline=None,
+              e2e=dict(value=value, unit=unit, h2d_bytes_per_step=int(st.h2d_bytes), d2h_bytes_per_step=int(st.d2h_bytes), seconds=t),
+              gpu_launches=int(launches), clocks=clocks, parity=parity, parity_max_rel=parity["parity_max_rel"]))
+
+
 _JSON_FD = None
 
 
@@ -265,12 +385,17 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + sorted(QUANTITY_WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison (sweeps only: the line says so)")
     ap.add_argument("--max-batch", type=int, default=0)
     args = ap.parse_args()
+    if args.workload in QUANTITY_WORKLOADS:
+        if args.impl == "reference":
+            emit(dict(impl="reference", unavailable="the reference arm is defined for the DOS workloads (BASELINE.json metric)"))
+            return
+        return run_quantity(args, args.workload, QUANTITY_WORKLOADS[args.workload])
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, w)
@@ -363,25 +488,28 @@ def main():
         energy = np.linspace(-3, 3, 1000)
         broadening = float(np.float32(np.pi)) * kpm.scaling_factors[0] / (M - 2)   # -> exactly M moments (Jackson)
         del kpm
-        times, h2d, d2h = [], 0, 0
+        times, set_times, h2d, d2h = [], [], 0, 0
         k2 = make_kpm()   # context + NCCL communicator: created once per process, like a user would
         for i in range(1 + max(1, min(args.steps, 2))):
             barrier()
             t0 = time.perf_counter()
-            k2.model = model                                 # host CSR -> scale / order / ELL build -> H2D upload
-            dos = k2.calc_dos(energy, broadening, num_random=R)   # moments + allreduce + reconstruction, result on the host
+            k2.model = model                                 # host CSR -> page-locked mirror + upload, locality ordering (rank 0, broadcast)
+            t_set = time.perf_counter() - t0
+            dos = k2.calc_dos(energy, broadening, num_random=R)   # device layout build, moments + allreduce + reconstruction, result on the host
             barrier()
             dt = max_over_ranks(time.perf_counter() - t0)
             st = k2.stats
             assert st.num_moments == M, (st.num_moments, M)
             if i > 0:
                 times.append(dt)
+                set_times.append(max_over_ranks(t_set))
                 h2d, d2h = st.h2d_bytes, st.d2h_bytes + dos.data.nbytes
         del k2
         e2e = dict(value=nnz * M * R / float(np.mean(times)), unit=UNIT, h2d_bytes_per_step=int(h2d),
-                   d2h_bytes_per_step=int(d2h), seconds=float(np.mean(times)),
-                   note="kpm.model = model (host CSR: scale, locality ordering, ELL build, H2D upload) + calc_dos (moments, "
-                        "allreduce, reconstruction, D2H) through the public API")
+                   d2h_bytes_per_step=int(d2h), seconds=float(np.mean(times)), set_model_seconds=float(np.mean(set_times)),
+                   note="kpm.model = model (host CSR mirrored into page-locked memory and uploaded, locality ordering on rank 0 + "
+                        "broadcast) + calc_dos (scale / relabel / ELL / packing on the device, moments, allreduce, reconstruction, "
+                        "D2H) through the public API")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:   # the CPU baseline is reported at N = 1 only

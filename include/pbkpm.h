@@ -102,6 +102,8 @@ typedef struct pbk_stats {
                                  first starter kernel to the moment copy-out, allreduce included) */
     int64_t bulk_launches;    /* step launches that ran the bulk-copy (TMA) staged kernel variant */
     int64_t res_launches;     /* step launches that ran the resident-tile kernel variant (x rows of a tile and its halo in shared memory) */
+    int64_t persist_launches; /* recursions run by the persistent kernel (one launch for all steps of one vector; small systems);
+                                 step_launches then counts the steps it executed */
     int64_t graph_launches;   /* recursions replayed as one CUDA graph (small, launch-bound systems); their kernels are
                                  still counted in kernel_launches / step_launches */
 } pbk_stats;

@@ -39,7 +39,8 @@ class Stats(C.Structure):
                 ("gemm_flops", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("batch", C.c_int32), ("num_batches", C.c_int32), ("moments_device_ms", C.c_double),
                 ("bulk_launches", C.c_int64),
-                ("res_launches", C.c_int64), ("graph_launches", C.c_int64)]
+                ("res_launches", C.c_int64), ("persist_launches", C.c_int64),
+                ("graph_launches", C.c_int64)]
 
 
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_int64, C.c_int64, C.c_void_p)

@@ -228,17 +228,19 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     identity_order = env_int("PBK_IDENTITY_ORDER", 0) != 0;
     coarse_sites = env_int("PBK_COARSE", 16);
     res_mode = static_cast<int>(env_int("PBK_RES", 1));
-    res_tile = env_int("PBK_RES_TILE", 512);
+    res_tile = env_int("PBK_RES_TILE", 384);
+    res_buffers = static_cast<int>(env_int("PBK_RES_BUFS", 1));
     res_row_bytes = static_cast<int>(env_int("PBK_RES_ROW", 64));
     res_ctas = static_cast<int>(env_int("PBK_RES_CTAS", 3));
     res_stages = static_cast<int>(env_int("PBK_RES_STAGES", 2));
-    if (res_tile < 64 || res_tile % 64 != 0) res_tile = 512;
+    if (res_tile < 64 || res_tile % 64 != 0) res_tile = 384;
     if (res_row_bytes < 16 || res_row_bytes % 16 != 0) res_row_bytes = 64;
     dev_build = static_cast<int>(env_int("PBK_DEVBUILD", 1));
     bcast_order = static_cast<int>(env_int("PBK_BCAST_ORDER", 1));
     macro_tiles = env_int("PBK_MACRO", 256);   // 65 k-site macro-blocks: +4 % on configs[1] in short runs, +1.5 % in the power-capped bench (profiles/r01_ab_order_v6.log)
     cone_mode = static_cast<int>(env_int("PBK_CONE", 1));
     graph_mode = static_cast<int>(env_int("PBK_GRAPH", 1));
+    persist_mode = static_cast<int>(env_int("PBK_PERSIST", 1));
     graph_max_bytes = 1e6 * static_cast<double>(env_int("PBK_GRAPH_MAX_MB", 64));
     PBK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (cudaEvent_t* e : {&ev0, &ev1, &ev2, &ev3, &ev_begin, &ev_end}) PBK_CUDA(cudaEventCreate(e));
@@ -772,7 +774,7 @@ bool Engine::build_layout_on_device(DeviceHamiltonian& dh, int mode, Scale s, co
 /// (a few passes of the counting kernel), then one kernel writes the sorted halo lists and the 16-bit codes.
 bool Engine::ensure_res_meta(DeviceHamiltonian& dh, int R) {
     if (!dh.res_enabled || !dh.valid) return false;
-    ResGeometry const geo = res_geometry(dtype, dh.ell.k, R, res_ctas, res_stages);
+    ResGeometry const geo = res_geometry(dtype, dh.ell.k, R, res_ctas, res_stages, res_buffers);
     if (dh.res_ntiles > 0 && dh.res_geo.row_bytes == geo.row_bytes) return true;
     if (dh.res_failed_row_bytes == geo.row_bytes) return false;
     auto fail = [&]() { dh.res_failed_row_bytes = geo.row_bytes; dh.res_ntiles = 0; return false; };
@@ -1215,9 +1217,11 @@ int Engine::pick_batch(int vectors, int extra_blocks) const {
     int const hard = 4096 / dtype_size(dtype);  // 256 chunks of 16 bytes per row
     cap = std::min(cap, hard);
     cap = std::min(cap, config.max_batch > 0 ? config.max_batch : 64);
-    // layouts ordered for the resident-tile kernel advance as many vectors per pass as its row width holds
-    if (natural.valid && natural.res_enabled && natural.res_failed_row_bytes != static_cast<uint32_t>(res_row_bytes))
-        cap = std::min(cap, std::max(1, res_row_bytes / dtype_size(dtype)));
+    // layouts ordered for the resident-tile kernel advance exactly as many vectors per pass as its row width holds (a
+    // ragged last pass is padded with zero lanes): one geometry, one set of tile metadata
+    int const res_lanes = std::max(1, res_row_bytes / dtype_size(dtype));
+    if (natural.valid && natural.res_enabled && natural.res_failed_row_bytes != static_cast<uint32_t>(res_row_bytes) &&
+        res_lanes <= cap && 2 * vectors >= res_lanes) return res_lanes;
     if (cap < 1) throw Error(PBK_RUNTIME_ERROR, "pbkpm: not enough device memory for one KPM vector pair");
     // a pass of more than one vector is padded to whole 16-byte chunks (lane_pad), so the batch itself must be a
     // multiple of the chunk width: buffers are sized for `rb` lanes and every launch uses lane_pad(lanes) <= rb
@@ -1285,6 +1289,32 @@ void Engine::run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_siz
     };
     // Small systems are launch-bound (a step is a few microseconds of work): capture the whole sequence once as a
     // CUDA graph and replay it on later runs with the same buffers and row counts.
+    // One vector of a system small enough for one resident grid: the whole recursion in ONE persistent launch (grid
+    // barrier per step instead of a kernel launch per step), kernels_persist.cu
+    if (persist_mode && R == 1 && !opt_size && !h.transient && nv == n && M / 2 >= 2) {
+        int const table_ctas = 2 * num_sms;
+        persist_table.ensure(sizeof(double) * 3 * static_cast<size_t>(M / 2) * table_ctas);
+        persist_barrier.ensure(64);
+        PersistArgs p;
+        p.h = h.ell; p.nrows = nv; p.buf0 = r0; p.buf1 = r1; p.steps = M / 2;
+        p.table = persist_table.as<double>(); p.table_ctas = table_ctas; p.barrier = persist_barrier.as<unsigned>();
+        p.mom = mom.as<double>(); p.M = M;
+        bool handled = false;
+        PBK_CUDA(launch_persistent_diagonal(dtype, p, num_sms, stream, &handled));
+        if (handled) {
+            launches += 2;
+            ++stats.persist_launches;
+            stats.step_launches += M / 2;
+            int const s = dtype_size(dtype);
+            stats.step_bytes += static_cast<double>(M / 2) * static_cast<double>(nv) * (h.ell.k * (s + 4.0) + 3.0 * s) - static_cast<double>(nv) * s;
+            PBK_CUDA(cudaEventRecord(ev3, stream));
+            PBK_CUDA(cudaEventSynchronize(ev3));
+            float ms = 0;
+            PBK_CUDA(cudaEventElapsedTime(&ms, ev2, ev3));
+            stats.step_ms += ms;
+            return;
+        }
+    }
     if (h.res_enabled && &h == &natural && !opt_size) ensure_res_meta(natural, R);   // before any capture: it synchronises
     bool const graphable = graph_mode && !h.transient && !h.res_enabled && M / 2 >= 8 &&
                            static_cast<double>(nv) * R * dtype_size(dtype) <= graph_max_bytes;
@@ -1340,16 +1370,17 @@ void Engine::run_offdiagonal(DeviceHamiltonian const& h, int M, bool opt_size, s
     void* r0 = vec_a.as();
     void* r1 = vec_b.as();
     PBK_CUDA(cudaEventRecord(ev2, stream));
-    int64_t init_rows = n;
+    int64_t const nv = h.vec_rows > 0 ? h.vec_rows : n;   // light-cone sub-systems are shorter than the system
+    int64_t init_rows = nv;
     if (opt_size) {
-        PBK_CUDA(cudaMemsetAsync(r1, 0, static_cast<size_t>(n) * dtype_size(dtype), stream));
+        PBK_CUDA(cudaMemsetAsync(r1, 0, static_cast<size_t>(nv) * dtype_size(dtype), stream));
         init_rows = h.map.data[std::min(h.map.last_index(), h.map.src_offset + 1)];
     }
     step(h, r0, r1, nullptr, init_rows, 1, false, false, 0.5, M, 0, FIN_NONE);
     collect(0, r0, 0.5);
     collect(1, r1, 1.0);
     for (int k = 2; k < M; ++k) {  // calc_moments::basic (off-diagonal), calc_moments.hpp:103-114
-        int64_t const rows = opt_size ? h.map.optimal_size(k, M) : n;
+        int64_t const rows = opt_size ? h.map.optimal_size(k, M) : nv;
         step(h, r1, r0, nullptr, rows, 1, true, false, 1.0, M, k, FIN_NONE);
         std::swap(r0, r1);
         collect(k, r1, 1.0);
@@ -1499,9 +1530,10 @@ void Engine::moments_dos(int M, int num_random, cd* out) {
         vec_b.ensure(block_bytes);
         stats.batch = rb;
         seed_stream(first);
+        bool const full_width = h.res_enabled && rb * dtype_size(dtype) == res_row_bytes;   // resident-tile passes keep one row width
         for (int b0 = 0; b0 < count; b0 += rb) {
             int const lanes = std::min(rb, count - b0);
-            int const R = lane_pad(lanes);
+            int const R = full_width ? rb : lane_pad(lanes);
             generate_random_block(h, lanes, R, vec_a.as());
             run_diagonal(h, R, M, false);
             PBK_CUDA(launch_accumulate_lanes(mom.as<double>(), lanes, M, acc.as<double>(), stream));
@@ -1878,6 +1910,53 @@ void Engine::moments_ldos(int M, const int32_t* idx, int nidx, cd* out) {
     progress(nidx, nidx);
 }
 
+/// Light cone of an off-diagonal Green's function <dest_j| T_n(H~) |src>, n < M: the breadth-first ball around `src`
+/// up to shell (M - 1 + dest_offset) / 2 + 1, where dest_offset is the shell of the farthest destination -- step n of the
+/// recursion only needs the rows within min(n, M - 1 - n + dest_offset) bonds of the source (SliceMap::index with
+/// src_offset = 0, OptimizedHamiltonian.hpp:67-77), and the ball has one more shell so that these rows are complete.
+/// Returns false when the ball would be most of the system or a destination is out of reach (then: full relabelling).
+static bool greens_cone(const int32_t* indptr, const int32_t* indices, int64_t n, int32_t src, std::vector<int32_t> const& dests, int M,
+                        std::vector<int32_t>& mark, Cone& c, std::vector<int32_t>& dest_pos, int& dest_offset) {
+    c = Cone();
+    c.queue.push_back(src);
+    mark[src] = 0;
+    c.borders = {1};
+    std::vector<int> dest_shell(dests.size(), -1);
+    size_t found = 0;
+    for (size_t j = 0; j < dests.size(); ++j) if (dests[j] == src) { dest_shell[j] = 0; ++found; }
+    size_t head = 0;
+    bool ok = true;
+    for (int shell = 1; shell <= M; ++shell) {
+        if (found == dests.size()) {
+            int far = 0;
+            for (int d : dest_shell) far = std::max(far, d);
+            if (shell > (M - 1 + far) / 2 + 1) break;       // the previous shell was the last one needed
+        }
+        if (static_cast<int64_t>(c.queue.size()) > n / 2) { ok = false; break; }
+        size_t const end = c.queue.size();
+        for (; head < end; ++head) {
+            int32_t const row = c.queue[head];
+            for (int p = indptr[row]; p < indptr[row + 1]; ++p) {
+                int32_t const col = indices[p];
+                if (mark[col] < 0) { mark[col] = static_cast<int32_t>(c.queue.size()); c.queue.push_back(col); }
+            }
+        }
+        if (c.queue.size() == end) { c.exhausted = true; break; }
+        c.borders.push_back(static_cast<int32_t>(c.queue.size()));
+        for (size_t j = 0; j < dests.size(); ++j) {
+            if (dest_shell[j] < 0 && mark[dests[j]] >= 0) { dest_shell[j] = shell; ++found; }
+        }
+    }
+    if (found != dests.size()) ok = false;                  // a destination outside the reach of M - 1 steps (or of the component)
+    dest_pos.clear();
+    dest_offset = 0;
+    if (ok) {
+        for (size_t j = 0; j < dests.size(); ++j) { dest_pos.push_back(mark[dests[j]]); dest_offset = std::max(dest_offset, dest_shell[j]); }
+    }
+    for (int32_t site : c.queue) mark[site] = -1;
+    return ok;
+}
+
 void Engine::moments_greens(int M, int row, const int32_t* cols, int ncols, cd* out) {
     check_num_moments(M);
     if (ncols < 1) throw Error(PBK_INVALID_ARGUMENT, "at least one column index is required");
@@ -1885,6 +1964,74 @@ void Engine::moments_greens(int M, int row, const int32_t* cols, int ncols, cd* 
     if (row < 0 || row >= n) throw Error(PBK_LOGIC_ERROR, "KPM::calc_greens(i,j): invalid value for i or j.");   // KPM.cpp:105-107
     for (int i = 0; i < ncols; ++i) if (cols[i] < 0 || cols[i] >= n) throw Error(PBK_LOGIC_ERROR, "KPM::calc_greens(i,j): invalid value for i or j.");
     Indices target{{row}, std::vector<int32_t>(cols, cols + ncols)};
+    if (config.optimal_size && cone_mode && target.is_diagonal()) {   // <i|T_n|i>: the LDOS recursion on the light cone of i
+        int32_t const site = row;
+        moments_ldos(M, &site, 1, out);
+        return;
+    }
+    // ---- off-diagonal on a light-cone sub-system cut out of the resident Hamiltonian (no relabelling of the full system) ----
+    if (config.optimal_size && cone_mode && dev_build) {
+        std::vector<int32_t> mark(static_cast<size_t>(n), -1), dest_pos;
+        Cone cone;
+        int dest_offset = 0;
+        if (greens_cone(h_indptr.data(), h_indices.data(), n, row, target.dest, M, mark, cone, dest_pos, dest_offset)) {
+            auto& hn = natural_hamiltonian();
+            int const s = dtype_size(dtype);
+            int const kell = hn.ell.k;
+            int64_t const nloc = static_cast<int64_t>(cone.queue.size());
+            int64_t const rows = cone.complete_rows();
+            int64_t const pitch = (rows + 31) / 32 * 32;
+            DeviceHamiltonian sub;
+            sub.transient = true;
+            sub.sliced = true;
+            sub.vec_rows = nloc;
+            sub.map = cone.map();
+            sub.map.dest_offset = std::min(dest_offset, sub.map.last_index());
+            sub.idx = Indices{{0}, dest_pos};
+            sub.original_idx = target;
+            sub.seconds = hn.seconds;
+            sub.ell.k = kell;
+            reset_stats(M, sub, true, 1);
+            // Stats of the reference count the rows of the *system* for the unoptimised figure
+            begin_moments();
+            auto ensure_room = [](DevBuf& b, size_t bytes) { if (bytes > b.bytes()) b.ensure(bytes + bytes / 4); };
+            ensure_room(cone_val, static_cast<size_t>(kell) * pitch * s);
+            ensure_room(cone_col, static_cast<size_t>(kell) * pitch * sizeof(int32_t));
+            ensure_room(cone_queue, sizeof(int32_t) * static_cast<size_t>(nloc));
+            ensure_room(vec_a, static_cast<size_t>(nloc) * s);
+            ensure_room(vec_b, static_cast<size_t>(nloc) * s);
+            if (cone_gmap_rows != n) {
+                cone_gmap.ensure(sizeof(int32_t) * n);
+                PBK_CUDA(cudaMemsetAsync(cone_gmap.as(), 0xff, sizeof(int32_t) * n, stream));
+                cone_gmap_rows = n;
+            }
+            const int32_t* perm = hn.reordered ? hn.perm.as<int32_t>() : nullptr;
+            PBK_CUDA(cudaMemcpyAsync(cone_queue.as(), cone.queue.data(), sizeof(int32_t) * nloc, cudaMemcpyHostToDevice, stream));
+            stats.h2d_bytes += static_cast<int64_t>(sizeof(int32_t) * nloc);
+            PBK_CUDA(launch_cone_mark(cone_queue.as<int32_t>(), nloc, perm, cone_gmap.as<int32_t>(), true, stream));
+            PBK_CUDA(launch_cone_extract(dtype, hn.ell, cone_queue.as<int32_t>(), perm, cone_gmap.as<int32_t>(), rows, cone_val.as(), cone_col.as<int32_t>(), pitch, stream));
+            PBK_CUDA(launch_cone_mark(cone_queue.as<int32_t>(), nloc, perm, cone_gmap.as<int32_t>(), false, stream));
+            launches += 3;
+            sub.ell = EllDev{cone_val.as(), cone_col.as<int32_t>(), rows, pitch, kell};
+            stats.batch = 1;
+            stats.num_batches = 1;
+            ensure_moment_buffers(std::max(ncols, 1), M);
+            idx_buf.ensure(sizeof(int32_t) * std::max(ncols, 1));
+            int32_t const zero = 0;
+            PBK_CUDA(cudaMemcpyAsync(idx_buf.as(), &zero, sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+            PBK_CUDA(launch_unit_starter(dtype, vec_a.as(), nloc, 1, idx_buf.as<int32_t>(), 1, stream));
+            PBK_CUDA(cudaMemcpyAsync(idx_buf.as(), dest_pos.data(), sizeof(int32_t) * ncols, cudaMemcpyHostToDevice, stream));
+            ++launches;
+            run_offdiagonal(sub, M, true, [&](int k, void* r, double scale) {
+                PBK_CUDA(launch_gather_moment(dtype, r, 1, idx_buf.as<int32_t>(), ncols, mom.as<double>(), M, k, scale, stream));
+                ++launches;
+            });
+            PBK_CUDA(cudaMemcpyAsync(out, mom.as(), sizeof(cd) * static_cast<size_t>(ncols) * M, cudaMemcpyDeviceToHost, stream));
+            stats.d2h_bytes += sizeof(cd) * static_cast<size_t>(ncols) * M;
+            end_moments();
+            return;
+        }
+    }
     auto& h = optimized_for(target);
     bool const opt = config.optimal_size != 0 && h.sliced;
     reset_stats(M, h, opt, 1);
@@ -1928,50 +2075,62 @@ void Engine::moments_kubo(int M, const float* left, const float* right, int num_
     upload_operator(vl, left, h);
     upload_operator(vr, right, h);
     int const s = dtype_size(dtype);
-    size_t const vbytes = static_cast<size_t>(n) * s;
-    size_t const row_pitch = (vbytes + 127) / 128 * 128;   // stack rows start on 128-byte boundaries (16-byte cp.async in K4)
-    size_t const stack_bytes = row_pitch * M;
+    int first = 0, count = 0;
+    shard(num_random, &first, &count);
+    // All random vectors of this rank advance together as the lanes of one N x R block (one pass over H and over the
+    // velocity operators serves them all), and the two M x (N R) stacks are contracted by ONE GEMM whose inner dimension
+    // runs over sites and lanes: mu = sum_r L_r R_r^H (Core.cpp:140-144 does the same vector by vector).  The lanes per
+    // pass are bounded by the memory of the two stacks.
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    if (2.0 * stack_bytes + 4.0 * vbytes > 0.9 * static_cast<double>(free_b)) {
-        throw Error(PBK_RUNTIME_ERROR, "pbkpm: the two num_moments x system_size Kubo-Bastin stacks do not fit in device memory");
-    }
+    double const per_lane = (2.0 * M + 5.0) * static_cast<double>(n) * s + 8.0 * static_cast<double>(n);
+    int lanes_cap = static_cast<int>(0.85 * static_cast<double>(free_b) / per_lane);
+    lanes_cap = std::min(lanes_cap, config.max_batch > 0 ? config.max_batch : 16);
+    int const vmax = 16 / s;
+    if (lanes_cap >= vmax) lanes_cap = lanes_cap / vmax * vmax;
+    if (lanes_cap < 1) throw Error(PBK_RUNTIME_ERROR, "pbkpm: the two num_moments x system_size Kubo-Bastin stacks do not fit in device memory");
+    int const nb = std::max(1, (std::max(count, 1) + lanes_cap - 1) / lanes_cap);
+    int rb = (std::max(count, 1) + nb - 1) / nb;
+    rb = std::min(lane_pad(rb), lanes_cap);
+    size_t const vbytes = static_cast<size_t>(n) * rb * s;                 // one N x rb block
+    size_t const row_pitch = (vbytes + 127) / 128 * 128;                   // stack rows start on 128-byte boundaries (16-byte cp.async in K4)
+    size_t const stack_bytes = row_pitch * M;
     begin_moments();
     progress(-1, num_random);
     DevBuf lstack(stack_bytes), rstack(stack_bytes), u(vbytes), mu(sizeof(cd) * static_cast<size_t>(M) * M);
-    DevBuf gemm_ws(kubo_gemm_workspace_bytes(dtype, M, n, num_sms));
+    DevBuf gemm_ws(kubo_gemm_workspace_bytes(dtype, M, static_cast<int64_t>(n) * rb, num_sms));
     vec_a.ensure(vbytes);
     vec_b.ensure(vbytes);
-    ensure_moment_buffers(1, M);
+    ensure_moment_buffers(rb, M);
     PBK_CUDA(cudaMemsetAsync(mu.as(), 0, mu.bytes(), stream));
-    int first = 0, count = 0;
-    shard(num_random, &first, &count);
     seed_stream(first);
-    stats.batch = 1;
+    stats.batch = rb;
     auto row_of = [&](DevBuf& st, int k) { return static_cast<void*>(st.as<char>() + static_cast<size_t>(k) * row_pitch); };
-    for (int j = 0; j < count; ++j) {
-        generate_random_block(h, 1, 1, u.as());
+    for (int b0 = 0; b0 < count; b0 += rb) {
+        int const lanes = std::min(rb, count - b0);
+        int const R = lane_pad(lanes);                     // padded lanes are zero vectors: they add nothing to mu
+        generate_random_block(h, lanes, R, u.as());
         PBK_CUDA(cudaEventRecord(ev2, stream));
         // left: starter v_l|r>, rows are T_n(H) v_l |r>            (Core.cpp:131-133, DenseMatrixCollector)
         void* r0 = vec_a.as(); void* r1 = vec_b.as();
-        step(vl, u.as(), r0, nullptr, n, 1, false, false, 1.0, M, 0, FIN_NONE);
-        step(vl, u.as(), row_of(lstack, 0), nullptr, n, 1, false, false, 0.5, M, 0, FIN_NONE);
-        step(h, r0, r1, row_of(lstack, 1), n, 1, false, false, 0.5, M, 0, FIN_NONE);
-        for (int k = 2; k < M; ++k) { step(h, r1, r0, row_of(lstack, k), n, 1, true, false, 1.0, M, k, FIN_NONE); std::swap(r0, r1); }
+        step(vl, u.as(), r0, nullptr, n, R, false, false, 1.0, M, 0, FIN_NONE);
+        step(vl, u.as(), row_of(lstack, 0), nullptr, n, R, false, false, 0.5, M, 0, FIN_NONE);
+        step(h, r0, r1, row_of(lstack, 1), n, R, false, false, 0.5, M, 0, FIN_NONE);
+        for (int k = 2; k < M; ++k) { step(h, r1, r0, row_of(lstack, k), n, R, true, false, 1.0, M, k, FIN_NONE); std::swap(r0, r1); }
         // right: starter |r>, rows are v_r T_n(H)|r>                 (Core.cpp:135-137)
         r0 = u.as(); r1 = vec_b.as();
-        step(vr, r0, row_of(rstack, 0), nullptr, n, 1, false, false, 0.5, M, 0, FIN_NONE);
-        step(h, r0, r1, nullptr, n, 1, false, false, 0.5, M, 0, FIN_NONE);
-        step(vr, r1, row_of(rstack, 1), nullptr, n, 1, false, false, 1.0, M, 0, FIN_NONE);
+        step(vr, r0, row_of(rstack, 0), nullptr, n, R, false, false, 0.5, M, 0, FIN_NONE);
+        step(h, r0, r1, nullptr, n, R, false, false, 0.5, M, 0, FIN_NONE);
+        step(vr, r1, row_of(rstack, 1), nullptr, n, R, false, false, 1.0, M, 0, FIN_NONE);
         // r0 (= u) is overwritten from here on; its content is no longer needed
         for (int k = 2; k < M; ++k) {
-            step(h, r1, r0, nullptr, n, 1, true, false, 1.0, M, k, FIN_NONE);
+            step(h, r1, r0, nullptr, n, R, true, false, 1.0, M, k, FIN_NONE);
             std::swap(r0, r1);
-            step(vr, r1, row_of(rstack, k), nullptr, n, 1, false, false, 1.0, M, k, FIN_NONE);
+            step(vr, r1, row_of(rstack, k), nullptr, n, R, false, false, 1.0, M, k, FIN_NONE);
         }
         PBK_CUDA(cudaEventRecord(ev3, stream));
         double flops = 0;
-        PBK_CUDA(launch_kubo_gemm(dtype, lstack.as(), rstack.as(), M, n, static_cast<int64_t>(row_pitch), mu.as<double>(),
+        PBK_CUDA(launch_kubo_gemm(dtype, lstack.as(), rstack.as(), M, static_cast<int64_t>(n) * R, static_cast<int64_t>(row_pitch), mu.as<double>(),
                                   gemm_ws.as<double>(), gemm_ws.bytes(), num_sms, stream, &flops));
         launches += dtype_complex(dtype) ? 4 : 2;
         PBK_CUDA(cudaEventRecord(ev1, stream));
@@ -1983,7 +2142,7 @@ void Engine::moments_kubo(int M, const float* left, const float* right, int num_
         stats.gemm_ms += ms;
         stats.gemm_flops += flops;
         ++stats.num_batches;
-        progress(1, num_random);
+        progress(lanes, num_random);
     }
     allreduce(mu.as<double>(), 2LL * M * M);
     PBK_CUDA(cudaMemcpyAsync(out, mu.as(), mu.bytes(), cudaMemcpyDeviceToHost, stream));

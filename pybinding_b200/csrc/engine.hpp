@@ -241,7 +241,8 @@ private:
     int num_sms = 148;
     int step_tpb = 256, step_blocks_per_sm = 0, step_prefetch = 0, step_prefetch_mask = 0;
     int res_mode = 1;            // PBK_RES: resident-tile step kernel -- 0 off, 1 where the locality clusters are mostly surface, 2 always
-    int64_t res_tile = 512;      // PBK_RES_TILE: rows of a nominal resident tile (the locality clusters of such layouts)
+    int64_t res_tile = 384;      // PBK_RES_TILE: rows of a nominal resident tile (the locality clusters of such layouts)
+    int res_buffers = 1;         // PBK_RES_BUFS: resident-tile buffers per CTA (2: next tile loads during this one; slower: fewer warps)
     int res_row_bytes = 64;      // PBK_RES_ROW: bytes per row of a pass of the resident kernel (16 float lanes)
     int res_ctas = 3, res_stages = 2;   // PBK_RES_CTAS, PBK_RES_STAGES
     int64_t layout_tile = 0;     // cluster size of the current Hamiltonian's full-system layout
@@ -307,6 +308,8 @@ private:
     //      diagonal run is captured once and replayed, keyed by every baked-in pointer and row count ----
     struct RecursionGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0, step_launches = 0, bulk_launches = 0; double step_bytes = 0; };
     std::map<std::vector<int64_t>, RecursionGraph> graph_cache;
+    int persist_mode = 1;            // PBK_PERSIST=0: no persistent single-launch recursion for small systems
+    DevBuf persist_table, persist_barrier;
     int graph_mode = 1;
     double graph_max_bytes = 64e6;   // vector block size up to which a recursion counts as launch-bound
     void clear_graphs();

@@ -71,11 +71,12 @@ struct ResTile { int32_t row0, nrows, halo_off, nh; };   // rows [row0, row0 + n
 struct ResGeometry {
     uint32_t row_bytes = 0;        // bytes of one row of a vector block (lanes * sizeof scalar): the variant is built for one width
     uint32_t cb = 0, kvb = 0;      // bytes per row of the code records (uint16, padded to 16) and of the value records (padded to 16)
-    uint32_t xs_bytes = 0;         // shared memory of the resident tile
-    int cap_rows = 0;              // own + halo rows that fit
+    uint32_t xs_bytes = 0;         // shared memory of ONE resident-tile buffer
+    int cap_rows = 0;              // own + halo rows that fit in it
     int stages = 2, ctas_per_sm = 3, rows_per_iteration = 0;
+    int buffers = 1;               // resident-tile buffers per CTA (2: the next tile loads while this one is processed)
 };
-ResGeometry res_geometry(int dtype, int k, int lanes, int ctas_per_sm, int stages);
+ResGeometry res_geometry(int dtype, int k, int lanes, int ctas_per_sm, int stages, int buffers);
 int res_max_halo();
 /// nh_dev[t] = distinct rows outside tile t referenced by its rows (> res_max_halo(): too many to tell)
 cudaError_t launch_res_count(EllDev const& h, const ResTile* tiles_dev, int ntiles, int32_t* nh_dev, cudaStream_t s);
@@ -92,6 +93,19 @@ struct ResArgs {
 };
 /// y = H x - y with the fused sums (the step of the diagonal recursion); *handled == false: not applicable
 cudaError_t launch_step_res(int dtype, ResArgs const& a, int num_sms, cudaStream_t stream, LaunchInfo* info, bool* handled);
+
+// ---- persistent variant (kernels_persist.cu): the whole diagonal recursion of ONE vector of a small system in one launch ----
+struct PersistArgs {
+    EllDev h;
+    int64_t nrows = 0;
+    void* buf0 = nullptr; void* buf1 = nullptr;   // buf0 = r0 on entry; both are overwritten
+    int steps = 0;                                // M / 2
+    double* table = nullptr; int table_ctas = 0;  // [steps][table_ctas][3] doubles of scratch
+    unsigned* barrier = nullptr;                  // one word
+    double* mom = nullptr; int M = 0;             // c128 [M]
+};
+/// *handled == false: not applicable (system too large for one resident grid, unsupported ELL width)
+cudaError_t launch_persistent_diagonal(int dtype, PersistArgs const& a, int num_sms, cudaStream_t stream, bool* handled);
 
 /// Upper bound of blocks launch_step may use (size of the partials buffer = this * R * 3 doubles)
 int max_step_blocks(int num_sms);

@@ -42,7 +42,8 @@ struct ResDev {  // kernel parameters
     const void* x; void* y;
     int R, cpr, rpb, k, stages;
     uint32_t row_bytes, cb, kvb;  // bytes per row of a vector block / of the code records / of the value records
-    uint32_t xs_bytes, stage_bytes;
+    uint32_t xs_bytes, stage_bytes;   // xs_bytes: ONE resident-tile buffer; there are `buffers` of them
+    int buffers;                  // 2: the next tile is loaded while the current one is being processed
     double* partials; unsigned* counter; double* mom; double* m01; int M; int n; int fin;
 };
 
@@ -72,18 +73,19 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
     uint32_t const S = a.stages;
     uint32_t const row_bytes = a.row_bytes;
     uint32_t const smem0 = smem_u32(dyn_smem);
-    uint32_t const xs = smem0;                           // the resident tile: own rows, then halo rows
-    uint32_t const ring0 = smem0 + a.xs_bytes;
+    uint32_t const NB = static_cast<uint32_t>(a.buffers);
+    uint32_t const xs0 = smem0;                          // resident tiles: own rows, then halo rows; NB buffers
+    uint32_t const ring0 = smem0 + NB * a.xs_bytes;
     uint32_t const ring_end = ring0 + S * a.stage_bytes;
-    uint32_t const full0 = ring_end;                     // full[S], empty[S], xbar
+    uint32_t const full0 = ring_end;                     // full[S], empty[S], xbar[NB]
     uint32_t const empty_off = 8u * S;
-    uint32_t const xbar = full0 + 16u * S;
+    uint32_t const xbar0 = full0 + 16u * S;
     uint32_t const ybytes_full = rpb * row_bytes;        // stage layout: y | codes | values
     uint32_t const coff = ybytes_full, voff = ybytes_full + rpb * a.cb;
 
     if (tid == 0) {
         for (uint32_t st = 0; st < S; ++st) { mbar_init(full0 + 8u * st, 1u); mbar_init(full0 + empty_off + 8u * st, TPB / 32); }
-        mbar_init(xbar, 1u);
+        for (uint32_t b = 0; b < NB; ++b) mbar_init(xbar0 + 8u * b, TPB);   // every thread arrives with the bytes of the copies it issues
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -117,26 +119,56 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
 #pragma unroll
     for (int q = 0; q < NACC; ++q) acc[q] = 0.0;
 
-    uint32_t sb = ring0, fb = full0, cph = 0, xph = 0;
+    uint32_t sb = ring0, fb = full0, cph = 0;
     uint32_t const my_vec = tid * 16u;
     uint32_t const my_code = coff + ty * a.cb;
     uint32_t const my_val = voff + ty * a.kvb;
     uint32_t const kk = K > 0 ? static_cast<uint32_t>(K) : static_cast<uint32_t>(a.k);
 
-    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-        ResTile const tl = a.tiles[t];
-        uint32_t const nrows = static_cast<uint32_t>(tl.nrows), nh = static_cast<uint32_t>(tl.nh);
-        // the previous tile was read through the generic proxy, the next one is written by the bulk-copy engine (async
-        // proxy): a proxy fence by every reader, then the CTA barrier, orders the two
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) mbar_expect_tx(xbar, (nrows + nh) * row_bytes);
-        __syncthreads();                                   // the expectation is registered before any copy can complete
-        if (tid == 0) bulk_g2s(xs, xg_base + static_cast<size_t>(tl.row0) * row_bytes, nrows * row_bytes, xbar);
-        for (uint32_t j = tid; j < nh; j += TPB) {
-            int32_t const r = __ldg(a.halo_rows + tl.halo_off + j);
+    // The x rows of a tile -> resident buffer b: thread 0 copies the tile's own rows (one bulk copy), all threads share the
+    // halo rows (one small bulk copy each).  Every thread arrives on the buffer's barrier with the bytes it is about to
+    // copy, so the phase completes exactly when all of them have landed -- no CTA barrier between expectation and copies.
+    // The tile descriptor and the thread's first halo row numbers are fetched one tile ahead (`prefetch_tile`), so that
+    // nothing waits for a global load when the copies are issued.
+    constexpr uint32_t HPT = 3;                            // halo rows per thread held in registers (more: loaded late)
+    ResTile nxt{0, 0, 0, 0};
+    int32_t hidx[HPT];
+    auto prefetch_tile = [&](int t) {
+        nxt = a.tiles[t];
+#pragma unroll
+        for (uint32_t q = 0; q < HPT; ++q) {
+            uint32_t const j = tid + q * TPB;
+            hidx[q] = j < static_cast<uint32_t>(nxt.nh) ? __ldg(a.halo_rows + nxt.halo_off + j) : 0;
+        }
+    };
+    auto issue_tile = [&](uint32_t b) {
+        uint32_t const nrows = static_cast<uint32_t>(nxt.nrows), nh = static_cast<uint32_t>(nxt.nh);
+        uint32_t const xs = xs0 + b * a.xs_bytes, xbar = xbar0 + 8u * b;
+        uint32_t const mine = tid < nh ? (nh - tid + TPB - 1u) / TPB : 0u;      // halo rows tid, tid + TPB, ...
+        mbar_expect_tx(xbar, mine * row_bytes + (tid == 0 ? nrows * row_bytes : 0u));
+        if (tid == 0) bulk_g2s(xs, xg_base + static_cast<size_t>(nxt.row0) * row_bytes, nrows * row_bytes, xbar);
+#pragma unroll
+        for (uint32_t q = 0; q < HPT; ++q) {
+            uint32_t const j = tid + q * TPB;
+            if (j < nh) bulk_g2s(xs + (nrows + j) * row_bytes, xg_base + static_cast<size_t>(hidx[q]) * row_bytes, row_bytes, xbar);
+        }
+        for (uint32_t j = tid + HPT * TPB; j < nh; j += TPB) {
+            int32_t const r = __ldg(a.halo_rows + nxt.halo_off + j);
             bulk_g2s(xs + (nrows + j) * row_bytes, xg_base + static_cast<size_t>(r) * row_bytes, row_bytes, xbar);
         }
+    };
+    if (static_cast<int>(blockIdx.x) < a.ntiles) { prefetch_tile(blockIdx.x); issue_tile(0u); }
+    if (NB == 2u && static_cast<int>(blockIdx.x + gridDim.x) < a.ntiles) { prefetch_tile(blockIdx.x + gridDim.x); issue_tile(1u); }
+
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+        ResTile const tl = a.tiles[t];
+        uint32_t const nrows = static_cast<uint32_t>(tl.nrows);
+        uint32_t const b = NB == 2u ? (it & 1u) : 0u;
+        uint32_t const xs = xs0 + b * a.xs_bytes, xbar = xbar0 + 8u * b;
+        uint32_t const xph = NB == 2u ? ((it >> 1) & 1u) : (it & 1u);
+        int const tn = t + static_cast<int>(NB * gridDim.x);   // the tile that goes into this buffer next
+        if (tn < a.ntiles) prefetch_tile(tn);                  // its descriptor and halo row numbers: in flight during this tile
         bool xready = false;
 
         for (uint32_t r0 = 0; r0 < nrows; r0 += rpb) {
@@ -219,7 +251,12 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
             if (sb == ring_end) { sb = ring0; fb = full0; cph ^= 1u; }
         }
         if (!xready) mbar_wait(xbar, xph);   // (a tile without rows cannot occur; keeps the phase bookkeeping exact anyway)
-        xph ^= 1u;
+        // This buffer was read through the generic proxy and is refilled by the bulk-copy engine (async proxy): a proxy
+        // fence by every reader, then the CTA barrier, orders the two.  With two buffers the refill (the tile after next)
+        // overlaps the processing of the next tile, which is already resident or on its way.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tn < a.ntiles) issue_tile(b);
     }
 
     StepDev fin{};
@@ -366,7 +403,7 @@ cudaError_t launch_res_t(ResArgs const& a, int num_sms, cudaStream_t stream, Lau
     cudaError_t err = raise_res_limit(fn);
     if (err != cudaSuccess) return err;
     uint32_t const stage_bytes = (static_cast<uint32_t>(rpb) * (a.geo.row_bytes + a.geo.cb + a.geo.kvb) + 127u) / 128u * 128u;
-    int const dyn = static_cast<int>(a.geo.xs_bytes + a.geo.stages * stage_bytes + 16u * a.geo.stages + 16u);
+    int const dyn = static_cast<int>(a.geo.buffers * a.geo.xs_bytes + a.geo.stages * stage_bytes + 16u * a.geo.stages + 16u);
     if (dyn > RES_MAX_DYN) return cudaSuccess;
     int grid = num_sms * a.geo.ctas_per_sm;
     if (grid > a.ntiles) grid = a.ntiles;
@@ -376,6 +413,7 @@ cudaError_t launch_res_t(ResArgs const& a, int num_sms, cudaStream_t stream, Lau
     d.codes = static_cast<const unsigned char*>(a.codes); d.vals = static_cast<const unsigned char*>(a.vals);
     d.x = a.x; d.y = a.y; d.R = a.R; d.cpr = cpr; d.rpb = rpb; d.k = a.k; d.stages = a.geo.stages;
     d.row_bytes = a.geo.row_bytes; d.cb = a.geo.cb; d.kvb = a.geo.kvb; d.xs_bytes = a.geo.xs_bytes; d.stage_bytes = stage_bytes;
+    d.buffers = a.geo.buffers;
     d.partials = a.partials; d.counter = a.counter; d.mom = a.mom; d.m01 = a.m01; d.M = a.M; d.n = a.n; d.fin = a.fin;
     fn<<<grid, RES_TPB, dyn, stream>>>(d);
     *handled = true;
@@ -385,8 +423,9 @@ cudaError_t launch_res_t(ResArgs const& a, int num_sms, cudaStream_t stream, Lau
 
 } // anonymous namespace
 
-ResGeometry res_geometry(int dtype, int k, int lanes, int ctas_per_sm, int stages) {
+ResGeometry res_geometry(int dtype, int k, int lanes, int ctas_per_sm, int stages, int buffers) {
     ResGeometry g{};
+    g.buffers = buffers >= 2 ? 2 : 1;
     uint32_t const s = static_cast<uint32_t>(dtype_size(dtype));
     g.row_bytes = static_cast<uint32_t>(lanes) * s;
     g.cb = (2u * static_cast<uint32_t>(k) + 15u) / 16u * 16u;
@@ -399,7 +438,7 @@ ResGeometry res_geometry(int dtype, int k, int lanes, int ctas_per_sm, int stage
     // shared memory of one SM (227 KB opt-in, 1 KB reserved per CTA) shared by the resident CTAs; finish_sums holds 2 KB statically
     uint32_t const per_cta = (227u * 1024u) / static_cast<uint32_t>(g.ctas_per_sm) - 1024u - 2304u;
     uint32_t const fixed = g.stages * stage_bytes + 16u * g.stages + 16u;
-    g.xs_bytes = per_cta > fixed + 4096u ? (per_cta - fixed) / 128u * 128u : 0u;
+    g.xs_bytes = per_cta > fixed + 4096u ? (per_cta - fixed) / static_cast<uint32_t>(g.buffers) / 128u * 128u : 0u;
     g.cap_rows = g.row_bytes ? static_cast<int>(g.xs_bytes / g.row_bytes) : 0;
     if (g.cap_rows > 65535) { g.cap_rows = 65535; }     // 16-bit local codes
     g.rows_per_iteration = static_cast<int>(rpb);

@@ -385,6 +385,7 @@ PYBIND11_MODULE(_pbkpm, m) {
         .def_property_readonly("step_launches", [](Stats const& s) { return s.s.step_launches; })
         .def_property_readonly("bulk_launches", [](Stats const& s) { return s.s.bulk_launches; })
         .def_property_readonly("res_launches", [](Stats const& s) { return s.s.res_launches; })
+        .def_property_readonly("persist_launches", [](Stats const& s) { return s.s.persist_launches; })
         .def_property_readonly("graph_launches", [](Stats const& s) { return s.s.graph_launches; })
         .def_property_readonly("step_ms", [](Stats const& s) { return s.s.step_ms; })
         .def_property_readonly("step_bytes", [](Stats const& s) { return s.s.step_bytes; })

@@ -23,7 +23,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.complex64): 1e-5,
        np.dtype(np.float64): 1e-11, np.dtype(np.complex128): 1e-11}
-KNOBS = ("PBK_RES", "PBK_RES_TILE", "PBK_RES_ROW", "PBK_RES_CTAS", "PBK_RES_STAGES", "PBK_RELEASE", "PBK_DEVBUILD", "PBK_BULK", "PBK_XS", "PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL",
+KNOBS = ("PBK_PERSIST", "PBK_RES", "PBK_RES_TILE", "PBK_RES_ROW", "PBK_RES_CTAS", "PBK_RES_STAGES", "PBK_RELEASE", "PBK_DEVBUILD", "PBK_BULK", "PBK_XS", "PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL",
          "PBK_CONE",
          "PBK_GRAPH", "PBK_GRAPH_MAX_MB")
 
@@ -225,25 +225,31 @@ def test_cone_ldos_many_sites_of_a_large_system():
 
 def test_graph_replay_of_small_recursions_is_bit_identical():
     """Launch-bound recursions (small systems) are captured once as a CUDA graph and replayed: same kernels, same
-    parameters, so the moments are bit-identical to plain launches, call after call, for DOS and LDOS"""
+    parameters, so the moments are bit-identical to plain launches, call after call, for DOS and for the light-cone
+    sliced recursion on the relabelled Hamiltonian (PBK_CONE=0).  (A single vector normally runs in the persistent
+    kernel instead: PBK_PERSIST=0 selects the launch-per-step path here.)"""
     model = pb.graphene_rectangle(40.0, dtype=np.float32)     # configs[0]: 61 k sites
     M = 1026
-    with knobs(PBK_GRAPH=0):
+    site = model.system.find_nearest([3, 4])
+    with knobs(PBK_GRAPH=0, PBK_PERSIST=0, PBK_CONE=0):
         plain_kpm = pb.kpm(model, energy_range=(-8.5, 8.5), silent=True)
         plain = plain_kpm.impl.moments_dos(M, 1)
-        assert plain_kpm.stats.graph_launches == 0
-        site = model.system.find_nearest([3, 4])
+        assert plain_kpm.stats.graph_launches == 0 and plain_kpm.stats.persist_launches == 0
         plain_ldos = pb.kpm(model, energy_range=(-8.5, 8.5), silent=True).impl.moments_greens(M, site, [site])
-    kpm = pb.kpm(model, energy_range=(-8.5, 8.5), silent=True)
-    for call in range(3):
-        mom = kpm.impl.moments_dos(M, 1)
-        s = kpm.stats
-        assert s.graph_launches == 1 and s.step_launches == M // 2 and s.kernel_launches > M // 2
-        assert np.array_equal(mom, plain), call
-    for call in range(2):   # light-cone sliced diagonal Green's function through the relabelled Hamiltonian
-        g = kpm.impl.moments_greens(M, site, [site])
-        assert kpm.stats.graph_launches == 1
-        assert np.array_equal(g, plain_ldos), call
+    with knobs(PBK_PERSIST=0, PBK_CONE=0):
+        kpm = pb.kpm(model, energy_range=(-8.5, 8.5), silent=True)
+        for call in range(3):
+            mom = kpm.impl.moments_dos(M, 1)
+            s = kpm.stats
+            assert s.graph_launches == 1 and s.step_launches == M // 2 and s.kernel_launches > M // 2
+            assert np.array_equal(mom, plain), call
+        for call in range(2):   # light-cone sliced diagonal Green's function through the relabelled Hamiltonian
+            g = kpm.impl.moments_greens(M, site, [site])
+            assert kpm.stats.graph_launches == 1
+            assert np.array_equal(g, plain_ldos), call
+    # the same diagonal element on the light-cone sub-system (default path) carries the same numbers
+    cone = pb.kpm(model, energy_range=(-8.5, 8.5), silent=True).impl.moments_greens(M, site, [site])
+    assert rel_err(cone, plain_ldos) < 1e-12
     big = pb.graphene_rectangle(60.0, dtype=np.complex64, magnetic_field=100.0)
     with knobs(PBK_GRAPH_MAX_MB=1):
         k2 = pb.kpm(big, energy_range=(-8.5, 8.5), silent=True)
@@ -296,10 +302,41 @@ def test_resident_tile_kernel_matches_general_kernel_and_oracle(dtype, k):
     for kw in (dict(PBK_RES_TILE=128), dict(PBK_RES_TILE=64, PBK_RES_STAGES=4, PBK_RES_CTAS=1),
                dict(PBK_RES_TILE=256, PBK_RES_ROW=128, PBK_RES_CTAS=2), dict(PBK_RES_TILE=1024, PBK_RES_ROW=32, PBK_RES_CTAS=4)):
         res, s1 = dos_moments(model, er, M, R, PBK_RES=2, **kw)
-        full_passes = sum(1 for b in range(s1.num_batches))   # every pass (also the ragged one, padded to whole chunks) runs resident
-        assert s1.res_launches == (M // 2 - 1) * full_passes, "the resident-tile kernel did not run: {} {}".format(kw, s1.res_launches)
+        width = kw.get("PBK_RES_ROW", 64) // dtype.itemsize
+        assert s1.batch == width and s1.num_batches == -(-R // width)
+        # every pass (also the ragged one, padded with zero lanes to the full row width) runs the resident-tile kernel
+        assert s1.res_launches == (M // 2 - 1) * s1.num_batches, "the resident-tile kernel did not run: {} {}".format(kw, s1.res_launches)
         assert rel_err(res, expected) < TOL[dtype], kw
         assert rel_err(res, general) < (1e-12 if dtype.itemsize >= 8 and dtype != np.complex64 else 1e-6), kw
     again, _ = dos_moments(model, er, M, R, PBK_RES=2, PBK_RES_TILE=128)
     first, _ = dos_moments(model, er, M, R, PBK_RES=2, PBK_RES_TILE=128)
     assert np.array_equal(again, first), "moments must be bit-reproducible run to run"
+
+
+@pytest.mark.parametrize("k", [3, 4, 7])
+@pytest.mark.parametrize("dtype", [np.float32, np.complex64, np.float64, np.complex128], ids=lambda d: np.dtype(d).name)
+def test_persistent_kernel_matches_launch_per_step_and_oracle(dtype, k):
+    """`cheb_persistent` (kernels_persist.cu): the whole diagonal recursion of one vector in one cooperative launch with a
+    grid barrier per step, against one launch per step and the oracle; one, two and four rows per thread"""
+    dtype = np.dtype(dtype)
+    model, er = model_for(dtype, k)
+    M = 130
+    stepwise, s0 = dos_moments(model, er, M, 1, PBK_PERSIST=0)
+    assert s0.persist_launches == 0
+    single, s1 = dos_moments(model, er, M, 1)
+    assert s1.persist_launches == 1 and s1.step_launches == M // 2 and s1.graph_launches == 0
+    expected = OracleKPM(model.hamiltonian, energy_range=er, hp=True).dos_moments(M, 1)
+    assert rel_err(single, expected) < TOL[dtype]
+    assert rel_err(single, stepwise) < (1e-12 if dtype.itemsize >= 8 and dtype != np.complex64 else 1e-6)
+    again, _ = dos_moments(model, er, M, 1)
+    assert np.array_equal(single, again), "moments must be bit-reproducible run to run"
+    if k == 3 and dtype == np.float32:
+        for width, rows_per_thread in ((55.0, 2), (85.0, 4)):     # 115 k / 276 k sites: more than one row per thread
+            big = pb.graphene_rectangle(width, dtype=dtype)
+            a, sa = dos_moments(big, er, 66, 1)
+            b, sb = dos_moments(big, er, 66, 1, PBK_PERSIST=0)
+            assert sa.persist_launches == 1 and sb.persist_launches == 0, rows_per_thread
+            assert rel_err(a, b) < 1e-6
+        huge = pb.graphene_rectangle(120.0, dtype=dtype)          # 550 k sites: too many rows for one resident grid
+        _, sh = dos_moments(huge, er, 34, 1)
+        assert sh.persist_launches == 0
