@@ -1526,8 +1526,10 @@ void Engine::moments_dos(int M, int num_random, cd* out) {
         int const rb = pick_batch(count, 0);
         ensure_moment_buffers(rb, M);
         size_t const block_bytes = static_cast<size_t>(n) * rb * dtype_size(dtype);
+        double const t_alloc = now_seconds();
         vec_a.ensure(block_bytes);
         vec_b.ensure(block_bytes);
+        if (std::getenv("PBK_TIMING")) std::fprintf(stderr, "[pbkpm] moments_dos: vector blocks (2 x %.1f GB) ready after %.3f s\n", block_bytes / 1e9, now_seconds() - t_alloc);
         stats.batch = rb;
         seed_stream(first);
         bool const full_width = h.res_enabled && rb * dtype_size(dtype) == res_row_bytes;   // resident-tile passes keep one row width
@@ -2201,11 +2203,15 @@ void Engine::calc_dos(const double* energy, int ne, double broadening, int num_r
     auto const s = scaling_factors();
     int const M = required_num_moments(broadening);
     std::vector<cd> m(M);
+    double const t1 = now_seconds();
     moments_dos(M, num_random, m.data());
+    double const t2 = now_seconds();
     auto const g = damping_coefficients(config.kernel, config.lambda_value, M);
     for (int i = 0; i < M; ++i) m[i] *= g[i];
     spectral_density_device(m.data(), M, 1, 0, 1, energy, ne, s, out);
     last_total_seconds = now_seconds() - t0;
+    if (std::getenv("PBK_TIMING")) std::fprintf(stderr, "[pbkpm] calc_dos: setup %.3f s, moments_dos %.3f s (layout %.3f, moments phase wall %.3f, device %.3f), reconstruction %.3f s\n",
+                                                 t1 - t0, t2 - t1, stats.hamiltonian_time, stats.moments_time, stats.moments_device_ms * 1e-3, now_seconds() - t2);
 }
 
 void Engine::calc_ldos(const double* energy, int ne, double broadening, const int32_t* idx, int nidx, double* out) {

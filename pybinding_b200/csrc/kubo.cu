@@ -29,10 +29,11 @@ namespace {
 
 constexpr int BM = 128, BN = 128;       // CTA tile
 // warps: 4 (m) x WN (n); WN = 2: 8 warps with 32 x 64 warp tiles, WN = 4: 16 warps with 32 x 32 warp tiles
-constexpr int ROW_BYTES = 128;          // bytes of one operand row per pipeline stage
 constexpr int GEMM_STAGES = 3;
 
-template<class Real> struct Geom {
+// ROW_BYTES: bytes of one operand row per pipeline stage (128: 16 doubles, 256: 32 doubles -- half as many CTA barriers
+// per flop, 221 KB of shared memory for the three stages)
+template<class Real, int ROW_BYTES> struct Geom {
     static constexpr int TKE = ROW_BYTES / sizeof(Real);          // k-extent of a stage in elements
     static constexpr int PAD = sizeof(Real) == 8 ? 32 : 16;       // bytes: stride = 20 doubles / 36 floats
     static constexpr int STRIDE = ROW_BYTES + PAD;                // bytes between rows in shared memory
@@ -55,10 +56,10 @@ __device__ __forceinline__ double lds_as_double(uint32_t addr, float) { float v;
 
 /// part[z][Mp][Mp] = A[:, kz] * B[:, kz]^T  over the K-range of split z.  `ld` = row stride in real elements
 /// (a multiple of 16 bytes); kchunk is a multiple of the stage extent.
-template<class Real, bool IMAG, int WN>
+template<class Real, bool IMAG, int WN, int ROW_BYTES>
 __global__ void __launch_bounds__(128 * WN, 1) kubo_gemm_kernel(const Real* __restrict__ A, const Real* __restrict__ B, int M, int64_t K,
                                                                     int64_t ld, double* __restrict__ part, int Mp, int64_t kchunk) {
-    using G = Geom<Real>;
+    using G = Geom<Real, ROW_BYTES>;
     constexpr int TKE = G::TKE;
     constexpr int EPC = 16 / sizeof(Real);   // elements per 16-byte chunk
     extern __shared__ __align__(128) unsigned char gemm_smem[];
@@ -67,7 +68,8 @@ __global__ void __launch_bounds__(128 * WN, 1) kubo_gemm_kernel(const Real* __re
     constexpr int GEMM_THREADS = 128 * WN;
     constexpr int NB = BN / WN / 8;          // 8-column blocks per warp: 8 (WN = 2) or 4 (WN = 4)
     constexpr int WCOLS = BN / WN;
-    constexpr int LOADS = 1024 / GEMM_THREADS;  // 16-byte chunks per thread, per operand, per stage
+    constexpr int CPRW = ROW_BYTES / 16;                  // 16-byte chunks per operand row and stage
+    constexpr int LOADS = BM * CPRW / GEMM_THREADS;       // 16-byte chunks per thread, per operand, per stage
     int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int const wm = warp / WN, wn = warp % WN;
     int const m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -80,8 +82,8 @@ __global__ void __launch_bounds__(128 * WN, 1) kubo_gemm_kernel(const Real* __re
     int nj_cnt = (M - (n0 + wn * WCOLS) + 7) / 8; nj_cnt = nj_cnt < 0 ? 0 : (nj_cnt > NB ? NB : nj_cnt);
 
     // ---- producer side: each thread moves LOADS chunks of A and of B per stage ----
-    constexpr int RSTEP = GEMM_THREADS / 8;
-    int const lrow = tid >> 3, lch = tid & 7;            // rows lrow + RSTEP i, 16-byte chunk lch of the 128-byte row
+    constexpr int RSTEP = GEMM_THREADS / CPRW;
+    int const lrow = tid / CPRW, lch = tid % CPRW;       // rows lrow + RSTEP i, 16-byte chunk lch of the operand row
     auto load_stage = [&](int st, int slot) {
         int64_t const k0 = kbeg + static_cast<int64_t>(st) * TKE + lch * EPC;
         int64_t const left = (kend - k0) * static_cast<int64_t>(sizeof(Real));
@@ -175,9 +177,14 @@ __global__ void kubo_reduce_kernel(const double* part, int ksplit, int Mp, int M
     C[static_cast<int64_t>(i) * 2 + comp] += s;
 }
 
+static int gemm_row_bytes() {
+    static int const rb = [] { char const* v = std::getenv("PBK_KUBO_ROW"); return (v && std::atoi(v) == 128) ? 128 : 256; }();
+    return rb;
+}
+
 template<class Real>
 void gemm_plan(int M, int64_t N, bool cplx, int num_sms, int* Mp, int64_t* K, int* ksplit, int64_t* kchunk) {
-    using G = Geom<Real>;
+    using G = Geom<Real, 256>;   // split sizes in units of the larger stage extent (valid for both)
     int const tiles = (M + BM - 1) / BM;
     *Mp = tiles * BM;
     *K = cplx ? 2 * N : N;
@@ -195,13 +202,13 @@ void gemm_plan(int M, int64_t N, bool cplx, int num_sms, int* Mp, int64_t* K, in
     *kchunk = kc;
 }
 
-template<class Real, int WN>
+template<class Real, int WN, int ROW_BYTES>
 cudaError_t gemm_launch(const Real* a, const Real* b, int M, int64_t K, int64_t ld, bool cplx, double* C, double* part, int Mp, int ksplit,
                         int64_t kchunk, cudaStream_t s) {
-    using G = Geom<Real>;
+    using G = Geom<Real, ROW_BYTES>;
     static bool raised = false;
-    auto const k_re = kubo_gemm_kernel<Real, false, WN>;
-    auto const k_im = kubo_gemm_kernel<Real, true, WN>;
+    auto const k_re = kubo_gemm_kernel<Real, false, WN, ROW_BYTES>;
+    auto const k_im = kubo_gemm_kernel<Real, true, WN, ROW_BYTES>;
     if (!raised) {
         cudaError_t e = cudaFuncSetAttribute(k_re, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_im, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
@@ -231,8 +238,14 @@ cudaError_t gemm_t(const void* A, const void* B, int M, int64_t N, int64_t pitch
     static int const warps_n = [] { char const* v = std::getenv("PBK_KUBO_WN"); return (v && std::atoi(v) == 2) ? 2 : 4; }();
     auto const* a = static_cast<const Real*>(A);
     auto const* b = static_cast<const Real*>(B);
-    cudaError_t const err = warps_n == 2 ? gemm_launch<Real, 2>(a, b, M, K, ld, cplx, C, workspace, Mp, ksplit, kchunk, s)
-                                         : gemm_launch<Real, 4>(a, b, M, K, ld, cplx, C, workspace, Mp, ksplit, kchunk, s);
+    cudaError_t err;
+    if (gemm_row_bytes() == 128) {
+        err = warps_n == 2 ? gemm_launch<Real, 2, 128>(a, b, M, K, ld, cplx, C, workspace, Mp, ksplit, kchunk, s)
+                           : gemm_launch<Real, 4, 128>(a, b, M, K, ld, cplx, C, workspace, Mp, ksplit, kchunk, s);
+    } else {
+        err = warps_n == 2 ? gemm_launch<Real, 2, 256>(a, b, M, K, ld, cplx, C, workspace, Mp, ksplit, kchunk, s)
+                           : gemm_launch<Real, 4, 256>(a, b, M, K, ld, cplx, C, workspace, Mp, ksplit, kchunk, s);
+    }
     if (flops) *flops = 2.0 * M * M * static_cast<double>(K) * (cplx ? 2 : 1);
     return err;
 }
