@@ -578,12 +578,19 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
     };
 
     // ---- level 1: sites in block order (lvl1), block borders (bstart), block of every site (blk) ----
-    std::vector<int32_t> lvl1, blk(static_cast<size_t>(n));
+    // (large work arrays are left uninitialised: a value-initialising std::vector would zero -- and first-touch -- 150 MB
+    // each on this one thread; every entry is written by the parallel passes below)
+    std::vector<int32_t> lvl1_vec;
+    RawVec<int32_t> lvl1_raw, blk_raw;
+    blk_raw.resize_uninit(static_cast<size_t>(n));
+    int32_t* const blk = blk_raw.data();
+    const int32_t* lvl1 = nullptr;
     std::vector<int64_t> bstart;
     bool const use_coarse = coarse > 1 && macro % coarse == 0 && macro / coarse >= 1024 && n >= 8 * macro;   // blocks of >= 1024 super-nodes stay compact
     if (!use_coarse) {
         std::vector<int32_t> r1;
-        cluster_order_flat(n, indptr, indices, macro, lvl1, r1);
+        cluster_order_flat(n, indptr, indices, macro, lvl1_vec, r1);
+        lvl1 = lvl1_vec.data();
         for (int64_t b = 0; b * macro < n; ++b) bstart.push_back(b * macro);
         bstart.push_back(n);
         parallel_rows(n, [&](int64_t b, int64_t e) { for (int64_t i = b; i < e; ++i) blk[i] = static_cast<int32_t>(r1[i] / macro); });
@@ -593,7 +600,10 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
         // coarse adjacency with a fixed stride: at most CAP distinct neighbouring super-nodes, in first-occurrence order
         // (deterministic), unused slots point to the node itself (ignored by the ball growing)
         constexpr int CAP = 16;
-        std::vector<int32_t> cptr(static_cast<size_t>(ns) + 1), cidx(static_cast<size_t>(ns) * CAP);
+        if (ns * CAP >= (int64_t{1} << 31)) { cluster_order(n, indptr, indices, tile, queue, rmap, macro_tiles, 1); return; }
+        RawVec<int32_t> cptr, cidx;
+        cptr.resize_uninit(static_cast<size_t>(ns) + 1);
+        cidx.resize_uninit(static_cast<size_t>(ns) * CAP);
         std::atomic<bool> overflow{false};
         parallel_rows(ns, [&](int64_t b, int64_t e) {
             for (int64_t sn = b; sn < e; ++sn) {
@@ -610,11 +620,11 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
                     out[cnt++] = c;
                 }
                 for (int q = cnt; q < CAP; ++q) out[q] = static_cast<int32_t>(sn);
-                cptr[sn] = static_cast<int32_t>(sn * CAP);
+                cptr.data()[sn] = static_cast<int32_t>(sn * CAP);
             }
         });
-        cptr[ns] = static_cast<int32_t>(ns * CAP);
-        if (overflow || ns * CAP >= (int64_t{1} << 31)) {   // denser than a lattice: grow the macro-blocks on the real graph instead
+        cptr.data()[ns] = static_cast<int32_t>(ns * CAP);
+        if (overflow) {   // denser than a lattice: grow the macro-blocks on the real graph instead
             cluster_order(n, indptr, indices, tile, queue, rmap, macro_tiles, 1);
             return;
         }
@@ -632,7 +642,9 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
             order.erase(order.begin() + odd);
             order.push_back(odd);
         }
-        lvl1.resize(static_cast<size_t>(n));
+        lvl1_raw.resize_uninit(static_cast<size_t>(n));
+        int32_t* const lvl1_out = lvl1_raw.data();
+        lvl1 = lvl1_out;
         bstart.assign(1, 0);
         for (int64_t ob = 0; ob < nb; ++ob) {   // block sizes first, so that the expansion below can run block-parallel
             int64_t const b = order[ob];
@@ -649,7 +661,7 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
                 int64_t pos = bstart[ob];
                 for (int64_t j = b * mc; j < std::min<int64_t>(ns, (b + 1) * mc); ++j) {
                     int64_t const sn = q1c[j];
-                    for (int64_t i = sn * coarse; i < std::min<int64_t>(n, (sn + 1) * coarse); ++i) { lvl1[pos++] = static_cast<int32_t>(i); blk[i] = static_cast<int32_t>(ob); }
+                    for (int64_t i = sn * coarse; i < std::min<int64_t>(n, (sn + 1) * coarse); ++i) { lvl1_out[pos++] = static_cast<int32_t>(i); blk[i] = static_cast<int32_t>(ob); }
                 }
             }
         }, 2);

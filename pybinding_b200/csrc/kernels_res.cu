@@ -48,6 +48,13 @@ struct ResDev {  // kernel parameters
 };
 
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(__cvta_generic_to_global(src)) : "memory");
+}
+/// the barrier receives one arrival (counted in its initial count) once all cp.async of this thread so far have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
     uint4 t;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(addr));
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
 
     if (tid == 0) {
         for (uint32_t st = 0; st < S; ++st) { mbar_init(full0 + 8u * st, 1u); mbar_init(full0 + empty_off + 8u * st, TPB / 32); }
-        for (uint32_t b = 0; b < NB; ++b) mbar_init(xbar0 + 8u * b, TPB);   // every thread arrives with the bytes of the copies it issues
+        for (uint32_t b = 0; b < NB; ++b) mbar_init(xbar0 + 8u * b, TPB + 1u);   // every thread's halo chunks + thread 0's bulk copy of the own rows
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -125,37 +132,46 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
     uint32_t const my_val = voff + ty * a.kvb;
     uint32_t const kk = K > 0 ? static_cast<uint32_t>(K) : static_cast<uint32_t>(a.k);
 
-    // The x rows of a tile -> resident buffer b: thread 0 copies the tile's own rows (one bulk copy), all threads share the
-    // halo rows (one small bulk copy each).  Every thread arrives on the buffer's barrier with the bytes it is about to
-    // copy, so the phase completes exactly when all of them have landed -- no CTA barrier between expectation and copies.
+    // The x rows of a tile -> resident buffer b: thread 0 copies the tile's own rows (one bulk copy); the halo rows are
+    // scattered, so they move as 16-byte cp.async chunks -- thread (tx, ty) takes chunk tx of halo rows ty, ty + rpb, ... --
+    // which a whole warp issues in ONE instruction (a bulk copy per 64-byte row went through the uniform datapath one lane
+    // at a time: ~15 % of the kernel's stall samples sat in that loop, profiles/r02_ncu_cubic_res_r16_v1.csv).  Each thread
+    // then attaches its copies to the buffer's barrier (cp.async.mbarrier.arrive.noinc), thread 0 adds the expectation of
+    // the bulk copy: the phase completes exactly when everything has landed, no CTA barrier between issue and use.
     // The tile descriptor and the thread's first halo row numbers are fetched one tile ahead (`prefetch_tile`), so that
     // nothing waits for a global load when the copies are issued.
-    constexpr uint32_t HPT = 3;                            // halo rows per thread held in registers (more: loaded late)
+    constexpr uint32_t HPT = 8;                            // halo rows per thread held in registers (more: loaded late)
     ResTile nxt{0, 0, 0, 0};
     int32_t hidx[HPT];
     auto prefetch_tile = [&](int t) {
         nxt = a.tiles[t];
 #pragma unroll
         for (uint32_t q = 0; q < HPT; ++q) {
-            uint32_t const j = tid + q * TPB;
-            hidx[q] = j < static_cast<uint32_t>(nxt.nh) ? __ldg(a.halo_rows + nxt.halo_off + j) : 0;
+            uint32_t const j = ty + q * rpb;
+            hidx[q] = (active && j < static_cast<uint32_t>(nxt.nh)) ? __ldg(a.halo_rows + nxt.halo_off + j) : 0;
         }
     };
     auto issue_tile = [&](uint32_t b) {
         uint32_t const nrows = static_cast<uint32_t>(nxt.nrows), nh = static_cast<uint32_t>(nxt.nh);
         uint32_t const xs = xs0 + b * a.xs_bytes, xbar = xbar0 + 8u * b;
-        uint32_t const mine = tid < nh ? (nh - tid + TPB - 1u) / TPB : 0u;      // halo rows tid, tid + TPB, ...
-        mbar_expect_tx(xbar, mine * row_bytes + (tid == 0 ? nrows * row_bytes : 0u));
-        if (tid == 0) bulk_g2s(xs, xg_base + static_cast<size_t>(nxt.row0) * row_bytes, nrows * row_bytes, xbar);
+        if (tid == 0) {
+            mbar_expect_tx(xbar, nrows * row_bytes);
+            bulk_g2s(xs, xg_base + static_cast<size_t>(nxt.row0) * row_bytes, nrows * row_bytes, xbar);
+        }
+        if (active) {
+            uint32_t const dst0 = xs + nrows * row_bytes + tx * 16u;
+            const unsigned char* const src0 = xg_base + tx * 16u;
 #pragma unroll
-        for (uint32_t q = 0; q < HPT; ++q) {
-            uint32_t const j = tid + q * TPB;
-            if (j < nh) bulk_g2s(xs + (nrows + j) * row_bytes, xg_base + static_cast<size_t>(hidx[q]) * row_bytes, row_bytes, xbar);
+            for (uint32_t q = 0; q < HPT; ++q) {
+                uint32_t const j = ty + q * rpb;
+                if (j < nh) cp_async_16(dst0 + j * row_bytes, src0 + static_cast<size_t>(hidx[q]) * row_bytes);
+            }
+            for (uint32_t j = ty + HPT * rpb; j < nh; j += rpb) {
+                int32_t const r = __ldg(a.halo_rows + nxt.halo_off + j);
+                cp_async_16(dst0 + j * row_bytes, src0 + static_cast<size_t>(r) * row_bytes);
+            }
         }
-        for (uint32_t j = tid + HPT * TPB; j < nh; j += TPB) {
-            int32_t const r = __ldg(a.halo_rows + nxt.halo_off + j);
-            bulk_g2s(xs + (nrows + j) * row_bytes, xg_base + static_cast<size_t>(r) * row_bytes, row_bytes, xbar);
-        }
+        cp_async_arrive_noinc(xbar);
     };
     if (static_cast<int>(blockIdx.x) < a.ntiles) { prefetch_tile(blockIdx.x); issue_tile(0u); }
     if (NB == 2u && static_cast<int>(blockIdx.x + gridDim.x) < a.ntiles) { prefetch_tile(blockIdx.x + gridDim.x); issue_tile(1u); }
