@@ -74,7 +74,7 @@ class ClockSampler:
     """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs"""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,clocks.mem")
 
     def __init__(self, device):
         self.device = device
@@ -103,7 +103,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, mem, power, reasons = [], [], [], [], set()
         for line in self.lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
@@ -113,12 +113,55 @@ class ClockSampler:
                 mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                power.append(float(f[3]))
+                mem.append(float(f[9]))
+            except (ValueError, IndexError):
+                pass
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         busy = [c for c in sm if c > 0]
         return dict(sm_mhz=float(np.median(busy)) if busy else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), mem_mhz=float(np.median(mem)) if mem else None,
+                    power_w=float(np.median(power)) if power else None)
+
+
+def sustained_copy(device, seconds=4.0):
+    """Device-to-device copy bandwidth (read + write bytes) sustained for `seconds` -- the same measurement as
+    MEASURED_PEAKS.json's burst figure (torch b.copy_(a), 1 Gi bf16 elements) but held as long as a benchmark step, so it
+    runs at whatever clocks the board settles to under its power cap.  Explains the gap between the step kernel's share of
+    the burst peak in a short capture (ncu: 99 %) and in the long timed region; the roofline `peak` stays the burst figure."""
+    try:
+        import torch
+        dev = torch.device("cuda", device)
+        a = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
+        b = torch.empty_like(a)
+        a.zero_()
+        for _ in range(3):
+            b.copy_(a)
+        torch.cuda.synchronize(dev)
+        sampler = ClockSampler(device)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps, total_ms, total_reps = 200, 0.0, 0
+        while total_ms < seconds * 1e3:
+            e0.record()
+            for _ in range(reps):
+                b.copy_(a)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            total_ms += e0.elapsed_time(e1)
+            total_reps += reps
+        clocks = sampler.stop()
+        gbs = 2.0 * a.numel() * 2 * total_reps / (total_ms * 1e-3) / 1e9
+        del a, b
+        torch.cuda.empty_cache()
+        return dict(gbs=gbs, seconds=total_ms * 1e-3, sm_mhz=clocks.get("sm_mhz"), mem_mhz=clocks.get("mem_mhz"),
+                    power_w=clocks.get("power_w"), reasons=clocks.get("reasons"),
+                    how="torch b.copy_(a) over 1 Gi bf16 elements back to back, CUDA events (MEASURED_PEAKS.json's copy, sustained)")
+    except Exception as e:   # explanatory extra: never fails the benchmark
+        return dict(gbs=None, error=str(e))
 
 
 def measured_peak():
@@ -448,6 +491,7 @@ def main():
         moments = kpm.impl.moments_dos(M, R)
     sampler = ClockSampler(local_rank)
     step_times, wall_times, launches, step_ms, step_bytes, step_launches, starter_ms, bulk_launches = [], [], 0, 0.0, 0.0, 0, 0.0, 0
+    res_launches, persist_launches = 0, 0
     barrier()
     sampler.start()
     for _ in range(args.steps):
@@ -464,6 +508,8 @@ def main():
         step_bytes += s.step_bytes
         step_launches += s.step_launches
         bulk_launches += s.bulk_launches
+        res_launches += s.res_launches
+        persist_launches += s.persist_launches
         starter_ms += s.starter_ms
         batch = s.batch
     clocks = sampler.stop()
@@ -472,12 +518,20 @@ def main():
     parity = oracle.check(moments, w["dtype"]) if oracle else None   # joins the oracle thread before the e2e leg
 
     peak, peak_src = measured_peak()
+    if res_launches:
+        kernel_name = "cheb_step_res (fused SpMM + moments, x rows of a tile and its halo resident in shared memory, y / matrix records staged by cp.async.bulk)"
+    elif bulk_launches:
+        kernel_name = "cheb_step_bulk (fused SpMM + moments, operands staged by cp.async.bulk)"
+    elif persist_launches:
+        kernel_name = "cheb_persist (all steps of the recursion in one cooperative launch, rows in registers)"
+    else:
+        kernel_name = "cheb_step (fused SpMM + moments)"
     achieved = (step_bytes / step_launches) / (step_ms / step_launches * 1e-3) / 1e9 if step_launches else 0.0
     s_item = np.dtype(w["dtype"]).itemsize
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                     traffic=ncu_traffic(args.workload, batch), peak_source=peak_src,
-                    kernel="cheb_step_bulk (fused SpMM + moments, operands staged by cp.async.bulk)" if bulk_launches
-                    else "cheb_step (fused SpMM + moments)", staged_launches=int(bulk_launches),
+                    kernel=kernel_name, staged_launches=int(bulk_launches), resident_tile_launches=int(res_launches),
+                    persistent_launches=int(persist_launches),
                     algorithmic_bytes_per_launch=step_bytes / max(step_launches, 1),
                     launch_ms=step_ms / max(step_launches, 1), vectors_per_pass=batch,
                     bytes_model="rows*[k*(s+4) + 3*R*s], s={}".format(s_item))
@@ -510,6 +564,11 @@ def main():
                    note="kpm.model = model (host CSR mirrored into page-locked memory and uploaded, locality ordering on rank 0 + "
                         "broadcast) + calc_dos (scale / relabel / ELL / packing on the device, moments, allreduce, reconstruction, "
                         "D2H) through the public API")
+
+    if world == 1 and n * batch * s_item > 2e9:   # long, bandwidth-bound steps only: what does a plain copy sustain on this board right now?
+        roofline["sustained_copy"] = sustained_copy(local_rank)
+        if roofline["sustained_copy"].get("gbs"):
+            roofline["frac_of_sustained_copy"] = achieved / roofline["sustained_copy"]["gbs"]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:   # the CPU baseline is reported at N = 1 only

@@ -232,7 +232,7 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     res_buffers = static_cast<int>(env_int("PBK_RES_BUFS", 1));
     res_row_bytes = static_cast<int>(env_int("PBK_RES_ROW", 64));
     res_ctas = static_cast<int>(env_int("PBK_RES_CTAS", 3));
-    res_stages = static_cast<int>(env_int("PBK_RES_STAGES", 2));
+    res_stages = static_cast<int>(env_int("PBK_RES_STAGES", 3));
     if (res_tile < 64 || res_tile % 64 != 0) res_tile = 384;
     if (res_row_bytes < 16 || res_row_bytes % 16 != 0) res_row_bytes = 64;
     dev_build = static_cast<int>(env_int("PBK_DEVBUILD", 1));
@@ -1254,9 +1254,10 @@ void Engine::ensure_moment_buffers(int R, int M) {
 }
 
 void Engine::step(DeviceHamiltonian const& h, const void* x, void* y, void* y2, int64_t nrows, int R, bool subtract, bool sums,
-                  double scale, int M, int nstep, int fin) {
+                  double scale, int M, int nstep, int fin, int64_t y_block_stride, int64_t y2_block_stride) {
     StepArgs a;
     a.h = h.ell; a.x = x; a.y = y; a.y2 = y2; a.nrows = nrows; a.R = R; a.subtract = subtract; a.sums = sums; a.scale = scale;
+    a.y_block_stride = y_block_stride; a.y2_block_stride = y2_block_stride;
     a.partials = partials.as<double>(); a.counter = counter.as<unsigned>(); a.mom = mom.as<double>(); a.m01 = m01.as<double>();
     a.M = M; a.n = nstep; a.fin = fin;
     a.tile = h.tile; a.tpb = step_tpb; a.blocks_per_sm = step_blocks_per_sm; a.prefetch = step_prefetch; a.prefetch_mask = step_prefetch_mask;
@@ -2097,7 +2098,9 @@ void Engine::moments_kubo(int M, const float* left, const float* right, int num_
     // pass are bounded by the memory of the two stacks.
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    double const per_lane = (2.0 * M + 5.0) * static_cast<double>(n) * s + 8.0 * static_cast<double>(n);
+    KuboStackLayout const probe = kubo_stack_layout(dtype, M, 256);      // row stride (payload + pad) of this scalar type
+    double const pad = static_cast<double>(probe.row_stride) / 256.0;
+    double const per_lane = (2.0 * M * pad + 5.0) * static_cast<double>(n) * s + 8.0 * static_cast<double>(n);
     int lanes_cap = static_cast<int>(0.85 * static_cast<double>(free_b) / per_lane);
     lanes_cap = std::min(lanes_cap, config.max_batch > 0 ? config.max_batch : 16);
     int const vmax = 16 / s;
@@ -2107,44 +2110,49 @@ void Engine::moments_kubo(int M, const float* left, const float* right, int num_
     int rb = (std::max(count, 1) + nb - 1) / nb;
     rb = std::min(lane_pad(rb), lanes_cap);
     size_t const vbytes = static_cast<size_t>(n) * rb * s;                 // one N x rb block
-    size_t const row_pitch = (vbytes + 127) / 128 * 128;                   // stack rows start on 128-byte boundaries (16-byte cp.async in K4)
-    size_t const stack_bytes = row_pitch * M;
+    // the stacks are k-blocked (kubo.cu): the step kernel writes row m of a stack through a blocked destination
+    KuboStackLayout const layout = kubo_stack_layout(dtype, M, vbytes);
+    int64_t const bstride = layout.block_stride;
     begin_moments();
     progress(-1, num_random);
-    DevBuf lstack(stack_bytes), rstack(stack_bytes), u(vbytes), mu(sizeof(cd) * static_cast<size_t>(M) * M);
-    DevBuf gemm_ws(kubo_gemm_workspace_bytes(dtype, M, static_cast<int64_t>(n) * rb, num_sms));
+    DevBuf lstack(layout.bytes), rstack(layout.bytes), u(vbytes), mu(sizeof(cd) * static_cast<size_t>(M) * M);
+    DevBuf gemm_ws(kubo_gemm_workspace_bytes(M, layout.blocks, num_sms));
     vec_a.ensure(vbytes);
     vec_b.ensure(vbytes);
     ensure_moment_buffers(rb, M);
     PBK_CUDA(cudaMemsetAsync(mu.as(), 0, mu.bytes(), stream));
     seed_stream(first);
     stats.batch = rb;
-    auto row_of = [&](DevBuf& st, int k) { return static_cast<void*>(st.as<char>() + static_cast<size_t>(k) * row_pitch); };
+    auto row_of = [&](DevBuf& st, int k) { return static_cast<void*>(st.as<char>() + static_cast<size_t>(k) * layout.row_stride); };
     for (int b0 = 0; b0 < count; b0 += rb) {
         int const lanes = std::min(rb, count - b0);
         int const R = lane_pad(lanes);                     // padded lanes are zero vectors: they add nothing to mu
+        // the blocks this pass fills; the tail of the last one (past the end of the vectors) must read as zero
+        KuboStackLayout const used = kubo_stack_layout(dtype, M, static_cast<size_t>(n) * R * s);
+        PBK_CUDA(cudaMemsetAsync(lstack.as<char>() + static_cast<size_t>(used.blocks - 1) * bstride, 0, static_cast<size_t>(bstride), stream));
+        PBK_CUDA(cudaMemsetAsync(rstack.as<char>() + static_cast<size_t>(used.blocks - 1) * bstride, 0, static_cast<size_t>(bstride), stream));
         generate_random_block(h, lanes, R, u.as());
         PBK_CUDA(cudaEventRecord(ev2, stream));
         // left: starter v_l|r>, rows are T_n(H) v_l |r>            (Core.cpp:131-133, DenseMatrixCollector)
         void* r0 = vec_a.as(); void* r1 = vec_b.as();
         step(vl, u.as(), r0, nullptr, n, R, false, false, 1.0, M, 0, FIN_NONE);
-        step(vl, u.as(), row_of(lstack, 0), nullptr, n, R, false, false, 0.5, M, 0, FIN_NONE);
-        step(h, r0, r1, row_of(lstack, 1), n, R, false, false, 0.5, M, 0, FIN_NONE);
-        for (int k = 2; k < M; ++k) { step(h, r1, r0, row_of(lstack, k), n, R, true, false, 1.0, M, k, FIN_NONE); std::swap(r0, r1); }
+        step(vl, u.as(), row_of(lstack, 0), nullptr, n, R, false, false, 0.5, M, 0, FIN_NONE, bstride, 0);
+        step(h, r0, r1, row_of(lstack, 1), n, R, false, false, 0.5, M, 0, FIN_NONE, 0, bstride);
+        for (int k = 2; k < M; ++k) { step(h, r1, r0, row_of(lstack, k), n, R, true, false, 1.0, M, k, FIN_NONE, 0, bstride); std::swap(r0, r1); }
         // right: starter |r>, rows are v_r T_n(H)|r>                 (Core.cpp:135-137)
         r0 = u.as(); r1 = vec_b.as();
-        step(vr, r0, row_of(rstack, 0), nullptr, n, R, false, false, 0.5, M, 0, FIN_NONE);
+        step(vr, r0, row_of(rstack, 0), nullptr, n, R, false, false, 0.5, M, 0, FIN_NONE, bstride, 0);
         step(h, r0, r1, nullptr, n, R, false, false, 0.5, M, 0, FIN_NONE);
-        step(vr, r1, row_of(rstack, 1), nullptr, n, R, false, false, 1.0, M, 0, FIN_NONE);
+        step(vr, r1, row_of(rstack, 1), nullptr, n, R, false, false, 1.0, M, 0, FIN_NONE, bstride, 0);
         // r0 (= u) is overwritten from here on; its content is no longer needed
         for (int k = 2; k < M; ++k) {
             step(h, r1, r0, nullptr, n, R, true, false, 1.0, M, k, FIN_NONE);
             std::swap(r0, r1);
-            step(vr, r1, row_of(rstack, k), nullptr, n, R, false, false, 1.0, M, k, FIN_NONE);
+            step(vr, r1, row_of(rstack, k), nullptr, n, R, false, false, 1.0, M, k, FIN_NONE, bstride, 0);
         }
         PBK_CUDA(cudaEventRecord(ev3, stream));
         double flops = 0;
-        PBK_CUDA(launch_kubo_gemm(dtype, lstack.as(), rstack.as(), M, static_cast<int64_t>(n) * R, static_cast<int64_t>(row_pitch), mu.as<double>(),
+        PBK_CUDA(launch_kubo_gemm(dtype, lstack.as(), rstack.as(), M, static_cast<int64_t>(n) * R, used, mu.as<double>(),
                                   gemm_ws.as<double>(), gemm_ws.bytes(), num_sms, stream, &flops));
         launches += dtype_complex(dtype) ? 4 : 2;
         PBK_CUDA(cudaEventRecord(ev1, stream));

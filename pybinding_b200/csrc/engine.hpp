@@ -342,7 +342,7 @@ private:
     int lane_pad(int R) const;
     void ensure_moment_buffers(int R, int M);
     void step(DeviceHamiltonian const& h, const void* x, void* y, void* y2, int64_t nrows, int R, bool subtract, bool sums,
-              double scale, int M, int nstep, int fin);
+              double scale, int M, int nstep, int fin, int64_t y_block_stride = 0, int64_t y2_block_stride = 0);
     /// diagonal recursion for the R vectors in vec_a (r0); moments land in `mom` ([R][M] c128)
     void run_diagonal(DeviceHamiltonian const& h, int R, int M, bool opt_size);
     /// off-diagonal recursion for the single vector in vec_a; `collect(n, r, half)` is called for every moment

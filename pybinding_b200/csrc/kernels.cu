@@ -95,6 +95,13 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step(StepDev a) {
 #pragma unroll
     for (int q = 0; q < NACC; ++q) acc[q] = 0.0;
 
+    // y and the optional second destination; either may be a row of a k-blocked Kubo-Bastin stack (launch-uniform)
+    int64_t const y_bs = a.y_bs, y2_bs = a.y2_bs;
+    auto store_out = [&](int64_t ci, CH const& out) {
+        if (y_bs == 0) store_cs(y + ci, out); else store_cs(blocked_dst<CH>(a.y, ci, y_bs), out);
+        if (y2) { if (y2_bs == 0) store_cs(y2 + ci, out); else store_cs(blocked_dst<CH>(a.y2, ci, y2_bs), out); }
+    };
+
     if constexpr (K > 0) {
         int32_t c[KK]; T v[KK];
         if (row < a.nrows) {
@@ -133,8 +140,7 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step(StepDev a) {
                 out.e[e] = r;
                 if constexpr (SUMS) sums_(acc + e * C, xr.e[e], r);
             }
-            store_cs(y + row * cpr + tx, out);
-            if (y2) store_cs(y2 + row * cpr + tx, out);
+            store_out(row * cpr + tx, out);
 #pragma unroll
             for (int s = 0; s < KK; ++s) { c[s] = cn[s]; v[s] = vn[s]; }
             row = next;
@@ -165,8 +171,7 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step(StepDev a) {
 #pragma unroll
                 for (int e = 0; e < V; ++e) sums_(acc + e * C, xr.e[e], out.e[e]);
             }
-            store_cs(y + row * cpr + tx, out);
-            if (y2) store_cs(y2 + row * cpr + tx, out);
+            store_out(row * cpr + tx, out);
         }
     }
 
@@ -233,7 +238,8 @@ cudaError_t launch_step_t(StepArgs const& a, int num_sms, cudaStream_t stream, L
 
     StepDev d{a.h.val, a.h.col, a.h.pitch, a.h.k, a.x, a.y, a.y2, a.nrows, a.R, cpr, rpb,
               ipt, static_cast<int64_t>(grid - 1) * tile_rows, a.prefetch, a.prefetch_mask, a.scale,
-              a.partials, a.counter, a.mom, a.m01, a.M, a.n, a.fin};
+              a.partials, a.counter, a.mom, a.m01, a.M, a.n, a.fin, a.y_block_stride, a.y2_block_stride};
+    if (a.y_block_stride != 0 && a.subtract) return cudaErrorInvalidValue;   // a blocked y is write-only
     fn<<<grid, block, 0, stream>>>(d);
     if (info) { info->grid = grid; info->block = block; info->V = V; info->K = kused; info->bulk = 0; }
     return cudaGetLastError();

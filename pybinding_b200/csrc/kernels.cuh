@@ -27,6 +27,8 @@ struct StepArgs {
     const void* x = nullptr;   // N x R row-major block (gathered operand)
     void* y = nullptr;         // N x R block: read (SUB) and written
     void* y2 = nullptr;        // optional second destination, same layout as y
+    int64_t y_block_stride = 0;   // != 0: y (y2) is a row of a k-blocked Kubo-Bastin stack -- consecutive 256-byte blocks of the
+    int64_t y2_block_stride = 0;  //       vector lie this many bytes apart (general kernel only; a blocked y is write-only)
     int64_t nrows = 0;         // rows [0, nrows) are processed
     int R = 1;                 // vectors advanced together
     bool subtract = true;      // y = H*x - y   (else y = scale * H*x)
@@ -189,11 +191,16 @@ cudaError_t launch_random_transform(int dtype, const uint32_t* raw, int64_t n, i
                                     void* dst, cudaStream_t s);
 
 // ---- Kubo-Bastin contraction (kubo.cu) -------------------------------------------------------
-/// C (M x M, c128 row-major) += A (M x N) * B^H (N x M); A, B row-major stacks of the Hamiltonian's scalar type,
-/// rows `pitch_bytes` apart (a multiple of 16; base pointers 16-byte aligned).  `workspace` holds the split-K partial
-/// tiles (kubo_gemm_workspace_bytes).
-size_t kubo_gemm_workspace_bytes(int dtype, int M, int64_t N, int num_sms);
-cudaError_t launch_kubo_gemm(int dtype, const void* A, const void* B, int M, int64_t N, int64_t pitch_bytes, double* C_c128,
+/// The two M x N stacks are "k-blocked" (kubo.cu): block kb holds bytes [256 kb, 256 kb + 256) of every moment row, rows
+/// `row_stride` bytes apart (payload + pad), blocks `block_stride` = M * row_stride bytes apart.  Row m of the stack is
+/// written by the step kernel through StepArgs::y_block_stride / y2_block_stride with base = stack + m * row_stride.
+/// The bytes of the last block past the end of the vector must be zero.
+struct KuboStackLayout { int64_t blocks; int64_t block_stride; uint32_t row_stride; size_t bytes; };
+KuboStackLayout kubo_stack_layout(int dtype, int M, size_t vector_bytes);
+/// C (M x M, c128 row-major) += A (M x N) * B^H (N x M) for two k-blocked stacks of the Hamiltonian's scalar type
+/// (N = sites x lanes).  `workspace` holds the split-K partial tiles (kubo_gemm_workspace_bytes).
+size_t kubo_gemm_workspace_bytes(int M, int64_t blocks, int num_sms);
+cudaError_t launch_kubo_gemm(int dtype, const void* A, const void* B, int M, int64_t N, KuboStackLayout const& layout, double* C_c128,
                              double* workspace, size_t workspace_bytes, int num_sms, cudaStream_t s, double* flops);
 
 // ---- reconstruction (reconstruct.cu) ----------------------------------------------------------

@@ -25,6 +25,7 @@
 #include "bulk_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -33,6 +34,8 @@
 namespace pbk {
 
 namespace {
+
+constexpr uint32_t RES_DESC_CAP = 128;   // tile descriptors a CTA keeps in shared memory (2 KB)
 
 struct ResDev {  // kernel parameters
     const ResTile* tiles; int ntiles;
@@ -44,6 +47,7 @@ struct ResDev {  // kernel parameters
     uint32_t row_bytes, cb, kvb;  // bytes per row of a vector block / of the code records / of the value records
     uint32_t xs_bytes, stage_bytes;   // xs_bytes: ONE resident-tile buffer; there are `buffers` of them
     int buffers;                  // 2: the next tile is loaded while the current one is being processed
+    int l2_prefetch;              // the producer pulls the streamed operands of its next tile into L2
     double* partials; unsigned* counter; double* mom; double* m01; int M; int n; int fin;
 };
 
@@ -87,6 +91,7 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
     uint32_t const full0 = ring_end;                     // full[S], empty[S], xbar[NB]
     uint32_t const empty_off = 8u * S;
     uint32_t const xbar0 = full0 + 16u * S;
+    uint32_t const desc0 = xbar0 + 16u;                  // this CTA's tile descriptors (RES_DESC_CAP x 16 bytes)
     uint32_t const ybytes_full = rpb * row_bytes;        // stage layout: y | codes | values
     uint32_t const coff = ybytes_full, voff = ybytes_full + rpb * a.cb;
 
@@ -96,12 +101,41 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    // The descriptors of the tiles this CTA will work on (tile blockIdx.x + i gridDim.x is its i-th) are copied to shared
+    // memory once: producer and consumers then read them with ld.shared instead of waiting for a global load at every
+    // tile switch (8 % of the stall samples in profiles/r02_ncu_cubic_res_r16_v2.csv).  The launcher sizes the grid so
+    // that RES_DESC_CAP descriptors cover the CTA's share.
+    for (uint32_t i = tid; i < RES_DESC_CAP; i += TPB) {
+        int64_t const t = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x;
+        if (t < a.ntiles) {
+            int4 const d = __ldg(reinterpret_cast<const int4*>(a.tiles) + t);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc0 + 16u * i), "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w) : "memory");
+        }
+    }
     __syncthreads();
+    auto tile_desc = [&](uint32_t i) {   // descriptor of this CTA's i-th tile
+        uint4 const d = lds_u4(desc0 + 16u * i);
+        return ResTile{static_cast<int32_t>(d.x), static_cast<int32_t>(d.y), static_cast<int32_t>(d.z), static_cast<int32_t>(d.w)};
+    };
+    uint32_t const my_tiles = static_cast<int>(blockIdx.x) < a.ntiles ? (static_cast<uint32_t>(a.ntiles) - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
 
     // ---- producer (thread 0) of the y / record ring: walks (tile, block-iteration) in the consumers' order, S - 1 ahead ----
-    int pt = blockIdx.x;
+    // When it starts on a tile it also asks the bulk-copy engine to pull the streamed operands of its NEXT tile (y, codes,
+    // values, own x rows: ~70 KB) into L2, so that the ring -- only S - 1 stages deep, shared memory belongs to the x rows --
+    // is refilled at L2 latency rather than DRAM latency.
+    uint32_t pi = 0;                                     // index of the tile being produced among this CTA's tiles
     int32_t prow = 0, pleft = 0;
-    if (tid == 0 && pt < a.ntiles) { ResTile const t0 = a.tiles[pt]; prow = t0.row0; pleft = t0.nrows; }
+    auto prefetch_streams = [&](uint32_t i) {
+        if (i >= my_tiles || !a.l2_prefetch) return;
+        ResTile const t = tile_desc(i);
+        size_t const r0 = static_cast<size_t>(t.row0);
+        uint32_t const nr = static_cast<uint32_t>(t.nrows);
+        bulk_prefetch_l2(static_cast<const unsigned char*>(a.y) + r0 * row_bytes, nr * row_bytes);
+        bulk_prefetch_l2(xg_base + r0 * row_bytes, nr * row_bytes);
+        bulk_prefetch_l2(a.codes + r0 * a.cb, nr * a.cb);
+        bulk_prefetch_l2(a.vals + r0 * a.kvb, nr * a.kvb);
+    };
+    if (tid == 0 && my_tiles > 0) { ResTile const t0 = tile_desc(0); prow = t0.row0; pleft = t0.nrows; prefetch_streams(1); }
     uint32_t psb = ring0, pfb = full0, pround = 0;
     auto produce = [&]() {
         if (pround > 0) mbar_wait(pfb + empty_off, (pround - 1u) & 1u);
@@ -112,14 +146,14 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
         bulk_g2s(psb + voff, a.vals + static_cast<size_t>(prow) * a.kvb, rows * a.kvb, pfb);
         prow += static_cast<int32_t>(rows); pleft -= static_cast<int32_t>(rows);
         if (pleft == 0) {
-            pt += gridDim.x;
-            if (pt < a.ntiles) { ResTile const tn = a.tiles[pt]; prow = tn.row0; pleft = tn.nrows; }
+            ++pi;
+            if (pi < my_tiles) { ResTile const tn = tile_desc(pi); prow = tn.row0; pleft = tn.nrows; prefetch_streams(pi + 1u); }
         }
         psb += a.stage_bytes; pfb += 8u;
         if (psb == ring_end) { psb = ring0; pfb = full0; ++pround; }
     };
     if (tid == 0) {
-        for (uint32_t i = 0; i + 1 < S && pt < a.ntiles; ++i) produce();
+        for (uint32_t i = 0; i + 1 < S && pi < my_tiles; ++i) produce();
     }
 
     double acc[NACC];
@@ -140,11 +174,11 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
     // the bulk copy: the phase completes exactly when everything has landed, no CTA barrier between issue and use.
     // The tile descriptor and the thread's first halo row numbers are fetched one tile ahead (`prefetch_tile`), so that
     // nothing waits for a global load when the copies are issued.
-    constexpr uint32_t HPT = 8;                            // halo rows per thread held in registers (more: loaded late)
+    constexpr uint32_t HPT = 6;                            // halo rows per thread held in registers (more: loaded late)
     ResTile nxt{0, 0, 0, 0};
     int32_t hidx[HPT];
-    auto prefetch_tile = [&](int t) {
-        nxt = a.tiles[t];
+    auto prefetch_tile = [&](uint32_t i) {
+        nxt = tile_desc(i);
 #pragma unroll
         for (uint32_t q = 0; q < HPT; ++q) {
             uint32_t const j = ty + q * rpb;
@@ -173,22 +207,21 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
         }
         cp_async_arrive_noinc(xbar);
     };
-    if (static_cast<int>(blockIdx.x) < a.ntiles) { prefetch_tile(blockIdx.x); issue_tile(0u); }
-    if (NB == 2u && static_cast<int>(blockIdx.x + gridDim.x) < a.ntiles) { prefetch_tile(blockIdx.x + gridDim.x); issue_tile(1u); }
+    if (my_tiles > 0u) { prefetch_tile(0u); issue_tile(0u); }
+    if (NB == 2u && my_tiles > 1u) { prefetch_tile(1u); issue_tile(1u); }
 
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
-        ResTile const tl = a.tiles[t];
+    for (uint32_t it = 0; it < my_tiles; ++it) {
+        ResTile const tl = tile_desc(it);
         uint32_t const nrows = static_cast<uint32_t>(tl.nrows);
         uint32_t const b = NB == 2u ? (it & 1u) : 0u;
         uint32_t const xs = xs0 + b * a.xs_bytes, xbar = xbar0 + 8u * b;
         uint32_t const xph = NB == 2u ? ((it >> 1) & 1u) : (it & 1u);
-        int const tn = t + static_cast<int>(NB * gridDim.x);   // the tile that goes into this buffer next
-        if (tn < a.ntiles) prefetch_tile(tn);                  // its descriptor and halo row numbers: in flight during this tile
+        uint32_t const itn = it + NB;                          // the tile that goes into this buffer next
+        if (itn < my_tiles) prefetch_tile(itn);                // its halo row numbers: in flight during this tile
         bool xready = false;
 
         for (uint32_t r0 = 0; r0 < nrows; r0 += rpb) {
-            if (tid == 0 && pt < a.ntiles) produce();      // refill the stage consumed one iteration ago
+            if (tid == 0 && pi < my_tiles) produce();      // refill the stage consumed one iteration ago
             uint32_t const lrow = r0 + ty;                 // my row inside the tile
             bool const valid = active && lrow < nrows;
             uint32_t const ci = (static_cast<uint32_t>(tl.row0) + lrow) * cpr + tx;   // my chunk of y (launcher: < 2^32)
@@ -272,7 +305,7 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
         // overlaps the processing of the next tile, which is already resident or on its way.
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        if (tn < a.ntiles) issue_tile(b);
+        if (itn < my_tiles) issue_tile(b);
     }
 
     StepDev fin{};
@@ -419,17 +452,19 @@ cudaError_t launch_res_t(ResArgs const& a, int num_sms, cudaStream_t stream, Lau
     cudaError_t err = raise_res_limit(fn);
     if (err != cudaSuccess) return err;
     uint32_t const stage_bytes = (static_cast<uint32_t>(rpb) * (a.geo.row_bytes + a.geo.cb + a.geo.kvb) + 127u) / 128u * 128u;
-    int const dyn = static_cast<int>(a.geo.buffers * a.geo.xs_bytes + a.geo.stages * stage_bytes + 16u * a.geo.stages + 16u);
+    int const dyn = static_cast<int>(a.geo.buffers * a.geo.xs_bytes + a.geo.stages * stage_bytes + 16u * a.geo.stages + 16u + 16u * RES_DESC_CAP);
     if (dyn > RES_MAX_DYN) return cudaSuccess;
     int grid = num_sms * a.geo.ctas_per_sm;
     if (grid > a.ntiles) grid = a.ntiles;
     if (grid > max_step_blocks(num_sms)) grid = max_step_blocks(num_sms);
+    if (static_cast<int64_t>(grid) * RES_DESC_CAP < a.ntiles) return cudaSuccess;   // more tiles per CTA than its descriptor cache holds
     ResDev d{};
     d.tiles = a.tiles; d.ntiles = a.ntiles; d.halo_rows = a.halo_rows;
     d.codes = static_cast<const unsigned char*>(a.codes); d.vals = static_cast<const unsigned char*>(a.vals);
     d.x = a.x; d.y = a.y; d.R = a.R; d.cpr = cpr; d.rpb = rpb; d.k = a.k; d.stages = a.geo.stages;
     d.row_bytes = a.geo.row_bytes; d.cb = a.geo.cb; d.kvb = a.geo.kvb; d.xs_bytes = a.geo.xs_bytes; d.stage_bytes = stage_bytes;
     d.buffers = a.geo.buffers;
+    { char const* v = std::getenv("PBK_RES_L2PF"); d.l2_prefetch = v ? std::atoi(v) : 0; }   // experiment knob, read per launch (off: the prefetches queue ahead of the ring copies in the same engine, 0.68 vs 0.78 of the roofline)
     d.partials = a.partials; d.counter = a.counter; d.mom = a.mom; d.m01 = a.m01; d.M = a.M; d.n = a.n; d.fin = a.fin;
     fn<<<grid, RES_TPB, dyn, stream>>>(d);
     *handled = true;
@@ -453,7 +488,7 @@ ResGeometry res_geometry(int dtype, int k, int lanes, int ctas_per_sm, int stage
     uint32_t const stage_bytes = (rpb * (g.row_bytes + g.cb + g.kvb) + 127u) / 128u * 128u;
     // shared memory of one SM (227 KB opt-in, 1 KB reserved per CTA) shared by the resident CTAs; finish_sums holds 2 KB statically
     uint32_t const per_cta = (227u * 1024u) / static_cast<uint32_t>(g.ctas_per_sm) - 1024u - 2304u;
-    uint32_t const fixed = g.stages * stage_bytes + 16u * g.stages + 16u;
+    uint32_t const fixed = g.stages * stage_bytes + 16u * g.stages + 16u + 16u * RES_DESC_CAP;
     g.xs_bytes = per_cta > fixed + 4096u ? (per_cta - fixed) / static_cast<uint32_t>(g.buffers) / 128u * 128u : 0u;
     g.cap_rows = g.row_bytes ? static_cast<int>(g.xs_bytes / g.row_bytes) : 0;
     if (g.cap_rows > 65535) { g.cap_rows = 65535; }     // 16-bit local codes

@@ -7,18 +7,29 @@
 // peak 37.1 TFLOP/s (tools/probe/dmma_probe.cu, profiles/r01_fp64_mma_probe.jsonl).  f32/c64 stacks are widened
 // to fp64 when the fragments are read from shared memory, so every scalar type accumulates in double.
 //
-// Both stacks are K-major (each moment row is contiguous over the N sites), i.e. the "TN" case where
-// A and B fragments use the same access pattern.  Complex stacks are treated as real M x 2N matrices:
+// Stack layout ("k-blocked", written directly by the step kernel's blocked destinations, step_common.cuh): the inner
+// dimension (sites x lanes, real and imaginary parts interleaved for complex types) is cut into blocks of 256 bytes; block
+// kb holds those 256 bytes of all M moment rows one after the other, each followed by a pad that makes the fragment reads
+// bank-conflict free (row stride 288 bytes for doubles, 272 for floats):
+//     element (m, k) at  kb * (M * RS) + m * RS + (k mod TKE) * sizeof(Real),   kb = k / TKE,  TKE = 256 / sizeof(Real)
+// One pipeline stage of a 128-row operand tile is therefore ONE contiguous 36 KB range of global memory and arrives by one
+// bulk copy (TMA engine, mbarrier complete_tx) already in its padded shared-memory form.  The row-major M x N stacks of
+// the first version needed 256 separate 256-byte reads per stage, 12 MB apart: 4096 cp.async instructions per stage, poor
+// DRAM page and TLB locality, and edge tiles that cost as much as full ones (cuBLAS on that layout: 22.4 TFLOP/s at
+// M = 514, profiles/r02_cublas_dgemm.log).
+//
+// Complex stacks are treated as real M x 2N matrices:
 //   Re(mu) = A' * B'^T                      with A' = [.. ar_k, ai_k ..], B' = [.. br_k, bi_k ..]
 //   Im(mu) = A'' * B'^T                     with A'' = [.. ai_k, -ar_k ..]   (pair swap + negate on fragment load)
 //
-// Kernel: 128 x 128 tile per CTA (8 warps, 32 x 64 per warp = 32 DMMAs per k4-step out of 12 fragment loads),
-// operands streamed global -> shared by a 3-stage cp.async ring of 128-byte rows (16 doubles / 32 floats per
-// stage, zero-filled past the edges), padded row stride so that fragment loads are bank-conflict free.
-// M is rarely a multiple of the tile (the reference's num_moments is 4k+2): 8 x 8 blocks that lie entirely
-// outside the matrix are skipped, so the cost follows ceil(M/8)^2 blocks, not the padded tile area.
-// Split-K over N with per-split partial tiles and a fixed-order reduction keeps the result deterministic.
-#include "kernels.cuh"
+// Kernel: 128 x 128 tile per CTA; 8 warps (4 x 2, warp tile 32 x 64 = 32 DMMAs per k4-step out of 12 fragment loads);
+// lane 0 of warp 0 issues the two bulk copies of a stage.  Three stages; full / empty mbarriers per stage, so the warps
+// never meet at a CTA barrier and may drift a stage apart (tools/probe/gemm_loop_probe.cu: this main loop sustains
+// 36.9 TFLOP/s from shared memory).  M is rarely a multiple of the tile (the
+// reference's num_moments is 4k+2): edge tiles copy only their valid rows, warps whose 32 x 64 region lies outside the
+// matrix do not take part at all, and 8 x 8 blocks outside are skipped, so the cost follows ceil(M/8)^2 blocks.
+// Split-K over the blocks with per-split partial tiles and a fixed-order reduction keeps the result deterministic.
+#include "bulk_common.cuh"
 
 #include <cstdlib>
 #include <type_traits>
@@ -28,119 +39,122 @@ namespace pbk {
 namespace {
 
 constexpr int BM = 128, BN = 128;       // CTA tile
-// warps: 4 (m) x WN (n); WN = 2: 8 warps with 32 x 64 warp tiles, WN = 4: 16 warps with 32 x 32 warp tiles
 constexpr int GEMM_STAGES = 3;
+constexpr int CONSUMER_WARPS = 8;       // 4 (m) x 2 (n), warp tile 32 x 64
+constexpr int GEMM_THREADS = 32 * CONSUMER_WARPS;
+constexpr int BLOCK_BYTES = 256;        // payload of one stack row inside a k-block
+constexpr int EXT_MAX = 6;              // a remainder of up to this many rows / columns (M mod 128) is folded into the last full tiles
 
-// ROW_BYTES: bytes of one operand row per pipeline stage (128: 16 doubles, 256: 32 doubles -- half as many CTA barriers
-// per flop, 221 KB of shared memory for the three stages)
-template<class Real, int ROW_BYTES> struct Geom {
-    static constexpr int TKE = ROW_BYTES / sizeof(Real);          // k-extent of a stage in elements
-    static constexpr int PAD = sizeof(Real) == 8 ? 32 : 16;       // bytes: stride = 20 doubles / 36 floats
-    static constexpr int STRIDE = ROW_BYTES + PAD;                // bytes between rows in shared memory
-    static constexpr int TILE = BM * STRIDE;                      // one operand, one stage
+template<class Real> struct Geom {
+    static constexpr int TKE = BLOCK_BYTES / sizeof(Real);        // k-extent of a block in elements
+    static constexpr int PAD = sizeof(Real) == 8 ? 32 : 16;       // bytes: row stride = 36 doubles / 68 floats
+    static constexpr int RS = BLOCK_BYTES + PAD;                  // bytes between rows, in global and in shared memory
+    static constexpr int TILE = (BM + EXT_MAX) * RS;              // one operand, one stage (room for the folded remainder rows)
     static constexpr int STAGE = 2 * TILE;
-    static constexpr int SMEM = GEMM_STAGES * STAGE;
+    static constexpr int SMEM = GEMM_STAGES * STAGE + 16 * GEMM_STAGES;
 };
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {  // zero-fills past src_bytes
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ double lds_as_double(uint32_t addr, double) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ double lds_as_double(uint32_t addr, float) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return static_cast<double>(v); }
 
-/// part[z][Mp][Mp] = A[:, kz] * B[:, kz]^T  over the K-range of split z.  `ld` = row stride in real elements
-/// (a multiple of 16 bytes); kchunk is a multiple of the stage extent.
-template<class Real, bool IMAG, int WN, int ROW_BYTES>
-__global__ void __launch_bounds__(128 * WN, 1) kubo_gemm_kernel(const Real* __restrict__ A, const Real* __restrict__ B, int M, int64_t K,
-                                                                    int64_t ld, double* __restrict__ part, int Mp, int64_t kchunk) {
-    using G = Geom<Real, ROW_BYTES>;
-    constexpr int TKE = G::TKE;
-    constexpr int EPC = 16 / sizeof(Real);   // elements per 16-byte chunk
+/// part[z][Mp][Mp] = A[:, blocks of split z] * B[:, same blocks]^T.  A, B: k-blocked stacks (see above), `bs` = bytes
+/// between consecutive blocks (M * RS), `bpc` = blocks per split.  fold > 0: M = 128 t + fold with fold <= EXT_MAX and the
+/// grid has t x t tiles; the CTAs of the last tile row (column) also compute the `fold` remaining rows (columns).
+template<class Real, bool IMAG>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) kubo_gemm_kernel(const unsigned char* __restrict__ A, const unsigned char* __restrict__ B, int M,
+                                                                    int64_t nblk, int64_t bs, double* __restrict__ part, int Mp, int64_t bpc, int fold) {
+    using G = Geom<Real>;
+    constexpr int ES = sizeof(Real);
     extern __shared__ __align__(128) unsigned char gemm_smem[];
-    uint32_t const smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(gemm_smem));
+    uint32_t const smem0 = smem_u32(gemm_smem);
+    uint32_t const full0 = smem0 + GEMM_STAGES * G::STAGE, empty0 = full0 + 8 * GEMM_STAGES;
 
-    constexpr int GEMM_THREADS = 128 * WN;
-    constexpr int NB = BN / WN / 8;          // 8-column blocks per warp: 8 (WN = 2) or 4 (WN = 4)
-    constexpr int WCOLS = BN / WN;
-    constexpr int CPRW = ROW_BYTES / 16;                  // 16-byte chunks per operand row and stage
-    constexpr int LOADS = BM * CPRW / GEMM_THREADS;       // 16-byte chunks per thread, per operand, per stage
     int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int const wm = warp / WN, wn = warp % WN;
     int const m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    int64_t const kbeg = static_cast<int64_t>(blockIdx.z) * kchunk;
-    int64_t const kend = (kbeg + kchunk < K) ? kbeg + kchunk : K;
-    int const nstage = static_cast<int>((kend - kbeg + TKE - 1) / TKE);
+    int64_t const kb0 = static_cast<int64_t>(blockIdx.z) * bpc;
+    int64_t const kb1 = (kb0 + bpc < nblk) ? kb0 + bpc : nblk;
+    int const nstage = static_cast<int>(kb1 - kb0);
+    int const ext_a = (fold > 0 && blockIdx.y + 1 == gridDim.y) ? fold : 0;                 // folded remainder rows / columns of this CTA
+    int const ext_b = (fold > 0 && blockIdx.x + 1 == gridDim.x) ? fold : 0;
+    int const rows_a = (M - m0 < BM) ? M - m0 : BM, rows_b = (M - n0 < BN) ? M - n0 : BN;   // valid rows of the two 128-row operand tiles
+    int const active_m = (rows_a + 31) / 32, active_n = (rows_b + 63) / 64;                // consumer warps with work: wm < active_m, wn < active_n
 
-    // 8 x 8 blocks of this warp that intersect the matrix (warp-uniform)
-    int mi_cnt = (M - (m0 + wm * 32) + 7) / 8; mi_cnt = mi_cnt < 0 ? 0 : (mi_cnt > 4 ? 4 : mi_cnt);
-    int nj_cnt = (M - (n0 + wn * WCOLS) + 7) / 8; nj_cnt = nj_cnt < 0 ? 0 : (nj_cnt > NB ? NB : nj_cnt);
+    if (tid == 0) {
+        for (int st = 0; st < GEMM_STAGES; ++st) { mbar_init(full0 + 8 * st, 1u); mbar_init(empty0 + 8 * st, static_cast<uint32_t>(active_m * active_n)); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
 
-    // ---- producer side: each thread moves LOADS chunks of A and of B per stage ----
-    constexpr int RSTEP = GEMM_THREADS / CPRW;
-    int const lrow = tid / CPRW, lch = tid % CPRW;       // rows lrow + RSTEP i, 16-byte chunk lch of the operand row
-    auto load_stage = [&](int st, int slot) {
-        int64_t const k0 = kbeg + static_cast<int64_t>(st) * TKE + lch * EPC;
-        int64_t const left = (kend - k0) * static_cast<int64_t>(sizeof(Real));
-        uint32_t const kbytes = left <= 0 ? 0u : (left >= 16 ? 16u : static_cast<uint32_t>(left));
-        uint32_t const dst0 = smem0 + slot * G::STAGE + lrow * G::STRIDE + lch * 16;
-#pragma unroll
-        for (int i = 0; i < LOADS; ++i) {
-            int const r = lrow + RSTEP * i;
-            bool const okA = (m0 + r < M) && kbytes > 0, okB = (n0 + r < M) && kbytes > 0;
-            const Real* const srcA = okA ? A + static_cast<int64_t>(m0 + r) * ld + k0 : A;
-            const Real* const srcB = okB ? B + static_cast<int64_t>(n0 + r) * ld + k0 : B;
-            cp_async16(dst0 + i * RSTEP * G::STRIDE, srcA, okA ? kbytes : 0u);
-            cp_async16(dst0 + G::TILE + i * RSTEP * G::STRIDE, srcB, okB ? kbytes : 0u);
-        }
+    // ---- producer: lane 0 of warp 0 (always an active warp), two bulk copies per stage -- the valid rows of the A tile and
+    //      of the B tile, each with the folded remainder rows, which follow the tile's rows in the block.  It refills, at the
+    //      top of stage st, the slot that stage st - 1 occupied: the only wait in the CTA that involves all warps, and only
+    //      warp 0 takes it (a dedicated producer warp would cap the kernel at 168 registers: 9 warps put 3 on one scheduler).
+    uint32_t const bytes_a = static_cast<uint32_t>(rows_a + ext_a) * G::RS, bytes_b = static_cast<uint32_t>(rows_b + ext_b) * G::RS;
+    const unsigned char* const pa0 = A + kb0 * bs + static_cast<int64_t>(m0) * G::RS;
+    const unsigned char* const pb0 = B + kb0 * bs + static_cast<int64_t>(n0) * G::RS;
+    auto produce = [&](int st) {       // stage st -> slot st % GEMM_STAGES
+        int const slot = st % GEMM_STAGES, round = st / GEMM_STAGES;
+        if (round > 0) mbar_wait(empty0 + 8 * slot, static_cast<uint32_t>(round - 1) & 1u);
+        uint32_t const dst = smem0 + slot * G::STAGE, bar = full0 + 8 * slot;
+        mbar_expect_tx(bar, bytes_a + bytes_b);
+        bulk_g2s(dst, pa0 + st * bs, bytes_a, bar);
+        bulk_g2s(dst + G::TILE, pb0 + st * bs, bytes_b, bar);
     };
+    if (tid == 0) {
+        for (int st = 0; st < GEMM_STAGES - 1 && st < nstage; ++st) produce(st);
+    }
+
+    int const wm = warp >> 1, wn = warp & 1;
+    if (wm >= active_m || wn >= active_n) return;      // this warp's 32 x 64 region lies outside the matrix
+    constexpr int NB = 8;                               // 8-column blocks per warp
+    // 8 x 8 blocks of this warp that intersect the matrix (warp-uniform)
+    int mi_cnt = (M - (m0 + wm * 32) + 7) / 8; mi_cnt = mi_cnt > 4 ? 4 : mi_cnt;
+    int nj_cnt = (M - (n0 + wn * 64) + 7) / 8; nj_cnt = nj_cnt > NB ? NB : nj_cnt;
 
     double c[4][NB][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < NB; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
-
-#pragma unroll
-    for (int st = 0; st < GEMM_STAGES - 1; ++st) {
-        if (st < nstage) load_stage(st, st);
-        cp_async_commit();
-    }
+    // folded remainder: the extra 8-row block (rows 128.. of the A tile) against this warp's share of the columns -- the
+    // four warps of a column half take two 8-column blocks each -- and the extra 8-column block against two of the warp's
+    // four row blocks; the corner block goes to warp 0
+    double ea[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, eb[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, ec[2] = {0.0, 0.0};
 
     // fragment addresses: thread holds A[row = lane / 4][k = lane % 4] of each 8 x 4 block (B alike)
     int const fr = lane >> 2, fk = lane & 3;
     int const fkA = IMAG ? (fk ^ 1) : fk;                     // A'' = [ai, -ar]: neighbour element, sign by parity
     double const sgnA = (IMAG && (fk & 1)) ? -1.0 : 1.0;
-    uint32_t const offA = (wm * 32 + fr) * G::STRIDE + fkA * sizeof(Real);
-    uint32_t const offB = G::TILE + (wn * WCOLS + fr) * G::STRIDE + fk * sizeof(Real);
+    uint32_t const offA = (wm * 32 + fr) * G::RS + fkA * ES;
+    uint32_t const offB = G::TILE + (wn * 64 + fr) * G::RS + fk * ES;
+    // lanes whose row of the extra block lies past the remainder re-read its last valid row (their results are dropped)
+    uint32_t const offAe = (BM + (fr < ext_a ? fr : (ext_a > 0 ? ext_a - 1 : 0))) * G::RS + fkA * ES;
+    uint32_t const offBe = G::TILE + (BN + (fr < ext_b ? fr : (ext_b > 0 ? ext_b - 1 : 0))) * G::RS + fk * ES;
+    uint32_t const offBx = G::TILE + (wn * 64 + wm * 16 + fr) * G::RS + fk * ES;     // column blocks 2 wm, 2 wm + 1 of this half
+    uint32_t const offAx = (wm * 32 + wn * 16 + fr) * G::RS + fkA * ES;               // row blocks 2 wn, 2 wn + 1 of this warp
 
-    // main loop, instantiated twice: interior tiles run the branch-free version, tiles on the matrix edge skip the
-    // 8 x 8 blocks that lie outside (both conditions are CTA-uniform)
-    auto mainloop = [&](auto edge_tag) {
-        constexpr bool EDGE = decltype(edge_tag)::value;
-        int slot = 0;
+    // main loop: interior warps run the branch-free version, warps on the matrix edge skip the 8 x 8 blocks that lie
+    // outside; EA / EB add the folded remainder rows / columns (interior tiles only)
+    auto mainloop = [&](auto edge_tag, auto ea_tag, auto eb_tag) {
+        constexpr bool EDGE = decltype(edge_tag)::value, EA = decltype(ea_tag)::value, EB = decltype(eb_tag)::value;
+        int slot = 0; uint32_t round = 0;
         for (int st = 0; st < nstage; ++st) {
-            cp_async_wait<GEMM_STAGES - 2>();   // stage st has landed (for this thread's copies)
-            __syncthreads();                    // ... for everyone's; and everyone is done with the slot refilled below
-            {
-                int const nxt = st + GEMM_STAGES - 1;
-                int nslot = slot + GEMM_STAGES - 1; if (nslot >= GEMM_STAGES) nslot -= GEMM_STAGES;
-                if (nxt < nstage) load_stage(nxt, nslot);
-                cp_async_commit();
-            }
+            if (tid == 0 && st + GEMM_STAGES - 1 < nstage) produce(st + GEMM_STAGES - 1);
+            __syncwarp();
+            mbar_wait(full0 + 8 * slot, round & 1u);
             uint32_t const base = smem0 + slot * G::STAGE;
 #pragma unroll
-            for (int kk = 0; kk < TKE; kk += 4) {
+            for (int kk = 0; kk < G::TKE; kk += 4) {
                 double a[4], b[NB];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = sgnA * lds_as_double(base + offA + i * 8 * G::STRIDE + kk * sizeof(Real), Real{});
+                for (int i = 0; i < 4; ++i) a[i] = sgnA * lds_as_double(base + offA + i * 8 * G::RS + kk * ES, Real{});
 #pragma unroll
-                for (int j = 0; j < NB; ++j) b[j] = lds_as_double(base + offB + j * 8 * G::STRIDE + kk * sizeof(Real), Real{});
+                for (int j = 0; j < NB; ++j) b[j] = lds_as_double(base + offB + j * 8 * G::RS + kk * ES, Real{});
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (!EDGE || i < mi_cnt) {
@@ -149,23 +163,52 @@ __global__ void __launch_bounds__(128 * WN, 1) kubo_gemm_kernel(const Real* __re
                             if (!EDGE || j < nj_cnt) dmma_m8n8k4(c[i][j][0], c[i][j][1], a[i], b[j]);
                     }
                 }
+                double ae = 0.0, be = 0.0;
+                if constexpr (EA) {
+                    ae = sgnA * lds_as_double(base + offAe + kk * ES, Real{});
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) dmma_m8n8k4(ea[t][0], ea[t][1], ae, lds_as_double(base + offBx + t * 8 * G::RS + kk * ES, Real{}));
+                }
+                if constexpr (EB) {
+                    be = lds_as_double(base + offBe + kk * ES, Real{});
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) dmma_m8n8k4(eb[t][0], eb[t][1], sgnA * lds_as_double(base + offAx + t * 8 * G::RS + kk * ES, Real{}), be);
+                }
+                if constexpr (EA && EB) { if (warp == 0) dmma_m8n8k4(ec[0], ec[1], ae, be); }
             }
-            if (++slot == GEMM_STAGES) slot = 0;
+            release_stage(empty0 + 8 * slot, static_cast<uint32_t>(tid));   // proxy fence + one arrival per warp
+            if (++slot == GEMM_STAGES) { slot = 0; ++round; }
         }
     };
-    if (m0 + BM <= M && n0 + BN <= M) mainloop(std::false_type{});
-    else mainloop(std::true_type{});
-    cp_async_wait<0>();
+    using Y = std::true_type; using N = std::false_type;
+    if (mi_cnt != 4 || nj_cnt != NB) mainloop(Y{}, N{}, N{});
+    else if (ext_a && ext_b) mainloop(N{}, Y{}, Y{});
+    else if (ext_a) mainloop(N{}, Y{}, N{});
+    else if (ext_b) mainloop(N{}, N{}, Y{});
+    else mainloop(N{}, N{}, N{});
 
     double* out = part + static_cast<int64_t>(blockIdx.z) * Mp * Mp;
+    int const orow = lane >> 2, ocol = (lane & 3) * 2;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-            int const row = m0 + wm * 32 + i * 8 + (lane >> 2);
-            int const col = n0 + wn * WCOLS + j * 8 + (lane & 3) * 2;
+            int const row = m0 + wm * 32 + i * 8 + orow;
+            int const col = n0 + wn * 64 + j * 8 + ocol;
             *reinterpret_cast<double2*>(out + static_cast<int64_t>(row) * Mp + col) = make_double2(c[i][j][0], c[i][j][1]);
         }
+    if (ext_a) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+            *reinterpret_cast<double2*>(out + static_cast<int64_t>(m0 + BM + orow) * Mp + n0 + wn * 64 + (wm * 2 + t) * 8 + ocol) = make_double2(ea[t][0], ea[t][1]);
+    }
+    if (ext_b) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+            *reinterpret_cast<double2*>(out + static_cast<int64_t>(m0 + wm * 32 + (wn * 2 + t) * 8 + orow) * Mp + n0 + BN + ocol) = make_double2(eb[t][0], eb[t][1]);
+    }
+    if (ext_a && ext_b && warp == 0)
+        *reinterpret_cast<double2*>(out + static_cast<int64_t>(m0 + BM + orow) * Mp + n0 + BN + ocol) = make_double2(ec[0], ec[1]);
 }
 
 __global__ void kubo_reduce_kernel(const double* part, int ksplit, int Mp, int M, double* C, int comp) {
@@ -177,77 +220,56 @@ __global__ void kubo_reduce_kernel(const double* part, int ksplit, int Mp, int M
     C[static_cast<int64_t>(i) * 2 + comp] += s;
 }
 
-static int gemm_row_bytes() {
-    static int const rb = [] { char const* v = std::getenv("PBK_KUBO_ROW"); return (v && std::atoi(v) == 128) ? 128 : 256; }();
-    return rb;
+/// split-K plan: `tiles` x `tiles` x `ksplit` CTAs of `bpc` blocks each; `fold` = remainder rows folded into the last tiles
+void gemm_plan(int M, int64_t nblk, int num_sms, int* Mp, int* tiles, int* fold, int* ksplit, int64_t* bpc) {
+    int const up = (M + BM - 1) / BM;
+    *Mp = up * BM;
+    *fold = (M >= BM && M % BM >= 1 && M % BM <= EXT_MAX) ? M % BM : 0;
+    *tiles = *fold ? M / BM : up;
+    // a few waves of CTAs (one per SM).  The CTAs of full tiles dominate the run time, so their number is made a
+    // multiple of the SM count; each split costs one 128 x 128 partial tile of traffic, negligible next to its k-range
+    static int const waves = [] { char const* v = std::getenv("PBK_KUBO_WAVES"); int w = v ? std::atoi(v) : 16; return w < 1 ? 1 : w; }();
+    int const full = (M / BM) * (M / BM);
+    int const heavy = full > 0 ? full : (*tiles) * (*tiles);
+    int64_t ks = static_cast<int64_t>(waves) * num_sms / heavy;
+    int64_t const max_split = (nblk + 7) / 8;                          // at least 8 stages per CTA
+    if (ks > max_split) ks = max_split;
+    if (ks > 1024) ks = 1024;
+    if (ks < 1) ks = 1;
+    int64_t const per = (nblk + ks - 1) / ks;
+    *ksplit = static_cast<int>((nblk + per - 1) / per);
+    *bpc = per;
 }
 
 template<class Real>
-void gemm_plan(int M, int64_t N, bool cplx, int num_sms, int* Mp, int64_t* K, int* ksplit, int64_t* kchunk) {
-    using G = Geom<Real, 256>;   // split sizes in units of the larger stage extent (valid for both)
-    int const tiles = (M + BM - 1) / BM;
-    *Mp = tiles * BM;
-    *K = cplx ? 2 * N : N;
-    // split-K: a few waves of CTAs (one CTA per SM) so that neither the light edge tiles nor the last wave leave
-    // SMs idle for long; each split costs one 128 x 128 partial tile of traffic, negligible next to its k-range
-    static int const waves = [] { char const* v = std::getenv("PBK_KUBO_WAVES"); int w = v ? std::atoi(v) : 8; return w < 1 ? 1 : w; }();
-    int ks = (waves * num_sms + tiles * tiles - 1) / (tiles * tiles);
-    int64_t const max_split = (*K + 8 * G::TKE - 1) / (8 * G::TKE);   // at least 8 stages per CTA
-    if (ks > max_split) ks = static_cast<int>(max_split);
-    if (ks > 512) ks = 512;
-    if (ks < 1) ks = 1;
-    int64_t kc = (*K + ks - 1) / ks;
-    kc = (kc + G::TKE - 1) / G::TKE * G::TKE;
-    *ksplit = static_cast<int>((*K + kc - 1) / kc);
-    *kchunk = kc;
-}
-
-template<class Real, int WN, int ROW_BYTES>
-cudaError_t gemm_launch(const Real* a, const Real* b, int M, int64_t K, int64_t ld, bool cplx, double* C, double* part, int Mp, int ksplit,
-                        int64_t kchunk, cudaStream_t s) {
-    using G = Geom<Real, ROW_BYTES>;
+cudaError_t gemm_t(const void* A, const void* B, int M, int64_t nblk, bool cplx, double* C, double* workspace, size_t workspace_bytes,
+                   int num_sms, cudaStream_t s) {
+    using G = Geom<Real>;
+    if (reinterpret_cast<uintptr_t>(A) % 16 != 0 || reinterpret_cast<uintptr_t>(B) % 16 != 0 || nblk < 1) return cudaErrorInvalidValue;
+    int Mp = 0, tiles = 0, fold = 0, ksplit = 0;
+    int64_t bpc = 0;
+    gemm_plan(M, nblk, num_sms, &Mp, &tiles, &fold, &ksplit, &bpc);
+    if (workspace_bytes < sizeof(double) * static_cast<size_t>(ksplit) * Mp * Mp) return cudaErrorInvalidValue;
     static bool raised = false;
-    auto const k_re = kubo_gemm_kernel<Real, false, WN, ROW_BYTES>;
-    auto const k_im = kubo_gemm_kernel<Real, true, WN, ROW_BYTES>;
+    auto const k_re = kubo_gemm_kernel<Real, false>;
+    auto const k_im = kubo_gemm_kernel<Real, true>;
     if (!raised) {
         cudaError_t e = cudaFuncSetAttribute(k_re, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_im, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
         if (e != cudaSuccess) return e;
         raised = true;
     }
-    int const tiles = Mp / BM;
     dim3 const grid(tiles, tiles, ksplit);
-    k_re<<<grid, 128 * WN, G::SMEM, s>>>(a, b, M, K, ld, part, Mp, kchunk);
-    kubo_reduce_kernel<<<(M * M + 255) / 256, 256, 0, s>>>(part, ksplit, Mp, M, C, 0);
+    int64_t const bs = static_cast<int64_t>(M) * G::RS;
+    auto const* a = static_cast<const unsigned char*>(A);
+    auto const* b = static_cast<const unsigned char*>(B);
+    k_re<<<grid, GEMM_THREADS, G::SMEM, s>>>(a, b, M, nblk, bs, workspace, Mp, bpc, fold);
+    kubo_reduce_kernel<<<(M * M + 255) / 256, 256, 0, s>>>(workspace, ksplit, Mp, M, C, 0);
     if (cplx) {
-        k_im<<<grid, 128 * WN, G::SMEM, s>>>(a, b, M, K, ld, part, Mp, kchunk);
-        kubo_reduce_kernel<<<(M * M + 255) / 256, 256, 0, s>>>(part, ksplit, Mp, M, C, 1);
+        k_im<<<grid, GEMM_THREADS, G::SMEM, s>>>(a, b, M, nblk, bs, workspace, Mp, bpc, fold);
+        kubo_reduce_kernel<<<(M * M + 255) / 256, 256, 0, s>>>(workspace, ksplit, Mp, M, C, 1);
     }
     return cudaGetLastError();
-}
-
-template<class Real>
-cudaError_t gemm_t(const void* A, const void* B, int M, int64_t N, int64_t pitch_bytes, bool cplx, double* C, double* workspace,
-                   size_t workspace_bytes, int num_sms, cudaStream_t s, double* flops) {
-    if (pitch_bytes % 16 != 0 || reinterpret_cast<uintptr_t>(A) % 16 != 0 || reinterpret_cast<uintptr_t>(B) % 16 != 0) return cudaErrorInvalidValue;
-    int Mp = 0, ksplit = 0;
-    int64_t K = 0, kchunk = 0;
-    gemm_plan<Real>(M, N, cplx, num_sms, &Mp, &K, &ksplit, &kchunk);
-    if (workspace_bytes < sizeof(double) * static_cast<size_t>(ksplit) * Mp * Mp) return cudaErrorInvalidValue;
-    int64_t const ld = pitch_bytes / static_cast<int64_t>(sizeof(Real));
-    static int const warps_n = [] { char const* v = std::getenv("PBK_KUBO_WN"); return (v && std::atoi(v) == 2) ? 2 : 4; }();
-    auto const* a = static_cast<const Real*>(A);
-    auto const* b = static_cast<const Real*>(B);
-    cudaError_t err;
-    if (gemm_row_bytes() == 128) {
-        err = warps_n == 2 ? gemm_launch<Real, 2, 128>(a, b, M, K, ld, cplx, C, workspace, Mp, ksplit, kchunk, s)
-                           : gemm_launch<Real, 4, 128>(a, b, M, K, ld, cplx, C, workspace, Mp, ksplit, kchunk, s);
-    } else {
-        err = warps_n == 2 ? gemm_launch<Real, 2, 256>(a, b, M, K, ld, cplx, C, workspace, Mp, ksplit, kchunk, s)
-                           : gemm_launch<Real, 4, 256>(a, b, M, K, ld, cplx, C, workspace, Mp, ksplit, kchunk, s);
-    }
-    if (flops) *flops = 2.0 * M * M * static_cast<double>(K) * (cplx ? 2 : 1);
-    return err;
 }
 
 /// K7: sum_{m,n} mu_mn * Gamma_mn(E) / (1 - E^2)^2 for one energy sample per block, with
@@ -300,22 +322,32 @@ cudaError_t launch_kubo_gamma_sum(const double* mu_c128, int M, const double* sc
     return cudaGetLastError();
 }
 
-size_t kubo_gemm_workspace_bytes(int dtype, int M, int64_t N, int num_sms) {
-    int Mp = 0, ksplit = 0;
-    int64_t K = 0, kchunk = 0;
-    bool const cplx = dtype_complex(dtype);
-    if (dtype == F32 || dtype == C64) gemm_plan<float>(M, N, cplx, num_sms, &Mp, &K, &ksplit, &kchunk);
-    else gemm_plan<double>(M, N, cplx, num_sms, &Mp, &K, &ksplit, &kchunk);
+KuboStackLayout kubo_stack_layout(int dtype, int M, size_t vector_bytes) {
+    bool const single = dtype == F32 || dtype == C64;
+    KuboStackLayout l{};
+    l.row_stride = single ? Geom<float>::RS : Geom<double>::RS;
+    l.blocks = static_cast<int64_t>((vector_bytes + BLOCK_BYTES - 1) / BLOCK_BYTES);
+    l.block_stride = static_cast<int64_t>(M) * l.row_stride;
+    l.bytes = static_cast<size_t>(l.blocks) * static_cast<size_t>(l.block_stride);
+    return l;
+}
+
+size_t kubo_gemm_workspace_bytes(int M, int64_t blocks, int num_sms) {
+    int Mp = 0, tiles = 0, fold = 0, ksplit = 0;
+    int64_t bpc = 0;
+    gemm_plan(M, blocks, num_sms, &Mp, &tiles, &fold, &ksplit, &bpc);
     return sizeof(double) * static_cast<size_t>(ksplit) * Mp * Mp;
 }
 
-cudaError_t launch_kubo_gemm(int dtype, const void* A, const void* B, int M, int64_t N, int64_t pitch_bytes, double* C_c128,
+cudaError_t launch_kubo_gemm(int dtype, const void* A, const void* B, int M, int64_t N, KuboStackLayout const& layout, double* C_c128,
                              double* workspace, size_t workspace_bytes, int num_sms, cudaStream_t s, double* flops) {
+    bool const cplx = dtype_complex(dtype);
+    if (flops) *flops = 2.0 * M * M * static_cast<double>(N) * (cplx ? 4 : 1);
     switch (dtype) {
-        case F32: return gemm_t<float>(A, B, M, N, pitch_bytes, false, C_c128, workspace, workspace_bytes, num_sms, s, flops);
-        case C64: return gemm_t<float>(A, B, M, N, pitch_bytes, true, C_c128, workspace, workspace_bytes, num_sms, s, flops);
-        case F64: return gemm_t<double>(A, B, M, N, pitch_bytes, false, C_c128, workspace, workspace_bytes, num_sms, s, flops);
-        case C128: return gemm_t<double>(A, B, M, N, pitch_bytes, true, C_c128, workspace, workspace_bytes, num_sms, s, flops);
+        case F32: return gemm_t<float>(A, B, M, layout.blocks, false, C_c128, workspace, workspace_bytes, num_sms, s);
+        case C64: return gemm_t<float>(A, B, M, layout.blocks, true, C_c128, workspace, workspace_bytes, num_sms, s);
+        case F64: return gemm_t<double>(A, B, M, layout.blocks, false, C_c128, workspace, workspace_bytes, num_sms, s);
+        case C128: return gemm_t<double>(A, B, M, layout.blocks, true, C_c128, workspace, workspace_bytes, num_sms, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -103,7 +103,17 @@ struct StepDev {  // POD copy of StepArgs for the kernel
     int pfmask;                   // only chunks with (tx & pfmask) == 0 issue the prefetch (one request per line)
     double scale;
     double* partials; unsigned* counter; double* mom; double* m01; int M; int n; int fin;
+    // destinations inside a k-blocked Kubo-Bastin stack (kubo.cu): byte stride between consecutive 256-byte blocks of the
+    // vector, 0 = an ordinary contiguous N x R block
+    int64_t y_bs; int64_t y2_bs;
 };
+
+/// address of chunk `ci` of a vector whose consecutive 256-byte blocks lie `bs` bytes apart (row m of a k-blocked stack)
+template<class CH> __device__ __forceinline__ CH* blocked_dst(void* base, int64_t ci, int64_t bs) {
+    static_assert(256 % sizeof(CH) == 0, "chunks never straddle a block");
+    int64_t const o = ci * static_cast<int64_t>(sizeof(CH));
+    return reinterpret_cast<CH*>(static_cast<char*>(base) + (o >> 8) * bs + (o & 255));
+}
 
 // ------------------------------------------------------------------------------------------------
 // Tail of the fused step kernels: block reduction of the per-thread sums (fixed-order tree over the rows of

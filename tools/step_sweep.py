@@ -38,8 +38,7 @@ def main():
     for cfg in args.configs:
         env = dict(kv.split("=") for kv in cfg.split(",") if kv)
         max_batch = int(env.pop("MB", 0))   # pseudo-key: vectors per pass
-        for k in ("PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL", "PBK_BULK", "PBK_XS",
-                  "PBK_IDENTITY_ORDER", "PBK_MACRO", "PBK_COARSE", "PBK_DEVBUILD", "PBK_RES"):
+        for k in [k for k in os.environ if k.startswith("PBK_") and k != "PBK_TIMING"]:   # every config starts from the defaults
             os.environ.pop(k, None)
         os.environ.update(env)
         t0 = time.time()
