@@ -80,6 +80,13 @@ class ClockSampler:
         self.device = device
         self.proc = None
         self.lines = []
+        self.begin = 0.0
+
+    def mark_begin(self):
+        """Samples that arrive from now on count.  nvidia-smi is started ahead of the timed region (its start-up takes a
+        few hundred milliseconds during which driver calls of this process stall -- visible in sub-second steps) and the
+        samples of the warm-up are dropped here."""
+        self.begin = time.perf_counter()
 
     def start(self):
         try:
@@ -93,7 +100,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -104,7 +111,11 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, mem, power, reasons = [], [], [], [], set()
-        for line in self.lines:
+        lines = [(t, l) for t, l in self.lines if t >= self.begin]
+        nearest = not lines and bool(self.lines)
+        if nearest:   # the timed region was shorter than the sampling period: the sample right before it stands in
+            lines = self.lines[-1:]
+        for stamp, line in lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -123,8 +134,9 @@ class ClockSampler:
                     reasons.add(name)
         busy = [c for c in sm if c > 0]
         return dict(sm_mhz=float(np.median(busy)) if busy else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm), mem_mhz=float(np.median(mem)) if mem else None,
-                    power_w=float(np.median(power)) if power else None)
+                    reasons=sorted(reasons), samples=0 if nearest else len(sm), mem_mhz=float(np.median(mem)) if mem else None,
+                    power_w=float(np.median(power)) if power else None,
+                    **(dict(note="timed region shorter than the 200 ms sampling period: the last sample before it is reported") if nearest else {}))
 
 
 def sustained_copy(device, seconds=4.0):
@@ -359,12 +371,13 @@ def run_quantity(args, name, w):
         sys.stderr.write("bench.py: PARITY FAILED for {}: {}\n".format(name, parity))
         emit(dict(metric=metric, value=None, error="parity failed", parity=parity))
         sys.exit(1)
+    sampler.start()
     for _ in range(max(args.warmup, 1)):
         call()
     if q == "conductivity":
         gemm.update(ms=0.0, flops=0.0, step_ms=0.0)
     times, dev_ms, launches = [], [], 0
-    sampler.start()
+    sampler.mark_begin()
     for _ in range(args.steps):
         t0 = time.perf_counter()
         out = call()
@@ -393,7 +406,8 @@ def run_quantity(args, name, w):
     emit(dict(metric=metric, value=value, unit=unit, n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3,
               higher_is_better=True, scaling="strong", vs_baseline=None, dtype=w["dtype"], data="synthetic",
               config=dict(workload=w["text"], sites=int(n), nnz=int(nnz), moments=int(M),
-                          moments_device_ms=float(np.mean(dev_ms)), timing="wall clock around the public API call (host buffers in, curves out)"),
+                          moments_device_ms=float(np.mean(dev_ms)), step_seconds=[round(x, 4) for x in times],
+                          timing="wall clock around the public API call (host buffers in, curves out)"),
               roofline=roofline, cpu_baseline=None,
               e2e=dict(value=value, unit=unit, h2d_bytes_per_step=int(st.h2d_bytes), d2h_bytes_per_step=int(st.d2h_bytes), seconds=t),
               gpu_launches=int(launches), clocks=clocks, parity=parity, parity_max_rel=parity["parity_max_rel"]))
@@ -487,13 +501,14 @@ def main():
     kpm.impl.scaling_factors  # bounds known (explicit range): nothing to compute
     # ---- device-resident timing: Hamiltonian already in HBM, one step = the whole moments phase ----
     moments = None
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         moments = kpm.impl.moments_dos(M, R)
-    sampler = ClockSampler(local_rank)
     step_times, wall_times, launches, step_ms, step_bytes, step_launches, starter_ms, bulk_launches = [], [], 0, 0.0, 0.0, 0, 0.0, 0
     res_launches, persist_launches = 0, 0
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     for _ in range(args.steps):
         barrier()
         t0 = time.perf_counter()

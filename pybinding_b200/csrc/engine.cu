@@ -300,6 +300,7 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
         cluster_rmap.swap(natural.reorder_map);
     }
     has_h = false;
+    kubo_l.release(); kubo_r.release(); kubo_ws.release();
     clear_graphs();
     natural = DeviceHamiltonian();
     bfs_ready = BfsOrder();
@@ -1406,6 +1407,7 @@ void Engine::run_offdiagonal(DeviceHamiltonian const& h, int M, bool opt_size, s
 }
 
 void Engine::reset_stats(int M, DeviceHamiltonian const& h, bool opt_size, double multiplier) {  // Stats.cpp:31-47
+    if (!keep_kubo_buffers) { kubo_l.release(); kubo_r.release(); kubo_ws.release(); }   // a different quantity: the stacks' memory is free again
     int64_t const h2d = stats.h2d_bytes;
     stats = pbk_stats{};
     stats.h2d_bytes = h2d;
@@ -2084,8 +2086,11 @@ void Engine::moments_greens(int M, int row, const int32_t* cols, int ncols, cd* 
 void Engine::moments_kubo(int M, const float* left, const float* right, int num_random, cd* out) {
     check_num_moments(M);
     if (num_random < 1) throw Error(PBK_INVALID_ARGUMENT, "num_random must be positive");
+    double const t_kubo0 = now_seconds();
     auto& h = natural_hamiltonian();
+    keep_kubo_buffers = true;
     reset_stats(M, h, false, num_random);
+    keep_kubo_buffers = false;
     DeviceHamiltonian vl, vr;
     upload_operator(vl, left, h);
     upload_operator(vr, right, h);
@@ -2113,10 +2118,19 @@ void Engine::moments_kubo(int M, const float* left, const float* right, int num_
     // the stacks are k-blocked (kubo.cu): the step kernel writes row m of a stack through a blocked destination
     KuboStackLayout const layout = kubo_stack_layout(dtype, M, vbytes);
     int64_t const bstride = layout.block_stride;
+    double const t_alloc = now_seconds();
     begin_moments();
     progress(-1, num_random);
-    DevBuf lstack(layout.bytes), rstack(layout.bytes), u(vbytes), mu(sizeof(cd) * static_cast<size_t>(M) * M);
-    DevBuf gemm_ws(kubo_gemm_workspace_bytes(M, layout.blocks, num_sms));
+    // the stacks stay with the context between calls (sigma_xx then sigma_xy on one object): releasing and re-mapping
+    // 2 x 28 GB costs up to a second of host time per call; any other moments entry point gives them back (reset_stats)
+    kubo_l.ensure(layout.bytes);
+    kubo_r.ensure(layout.bytes);
+    DevBuf& lstack = kubo_l; DevBuf& rstack = kubo_r;
+    DevBuf u(vbytes), mu(sizeof(cd) * static_cast<size_t>(M) * M);
+    if (std::getenv("PBK_TIMING")) std::fprintf(stderr, "[pbkpm] moments_kubo: operators + sizing %.3f s, stacks (2 x %.1f GB) allocated in %.3f s\n",
+                                                 t_alloc - t_kubo0, layout.bytes / 1e9, now_seconds() - t_alloc);
+    kubo_ws.ensure(kubo_gemm_workspace_bytes(M, layout.blocks, num_sms));
+    DevBuf& gemm_ws = kubo_ws;
     vec_a.ensure(vbytes);
     vec_b.ensure(vbytes);
     ensure_moment_buffers(rb, M);
@@ -2269,7 +2283,9 @@ void Engine::calc_conductivity(const float* left, const float* right, const doub
     auto const s = scaling_factors();
     int const M = required_num_moments(broadening);
     std::vector<cd> m(static_cast<size_t>(M) * M);
+    double const t1 = now_seconds();
     moments_kubo(M, left, right, num_random, m.data());
+    double const t2 = now_seconds();
     auto const g = damping_coefficients(config.kernel, config.lambda_value, M);
     for (int i = 0; i < M; ++i) for (int j = 0; j < M; ++j) m[static_cast<size_t>(i) * M + j] *= g[i] * g[j];  // Kernel.hpp:49-56
 
@@ -2287,8 +2303,11 @@ void Engine::calc_conductivity(const float* left, const float* right, const doub
     std::vector<double> sum_nm(2 * static_cast<size_t>(num_points));
     PBK_CUDA(cudaMemcpyAsync(sum_nm.data(), sum_dev.as(), sizeof(cd) * num_points, cudaMemcpyDeviceToHost, stream));
     PBK_CUDA(cudaStreamSynchronize(stream));
+    double const t3 = now_seconds();
     reconstruct_kubo_bastin(sum_nm.data(), samples, mu, nmu, temperature, s, out);
     last_total_seconds = now_seconds() - t0;
+    if (std::getenv("PBK_TIMING")) std::fprintf(stderr, "[pbkpm] calc_conductivity: setup %.3f s, moments_kubo %.3f s (device %.3f: recursion %.3f, GEMM %.3f), damping + Gamma sum %.3f s, Fermi integration %.3f s\n",
+                                                 t1 - t0, t2 - t1, stats.moments_device_ms * 1e-3, stats.step_ms * 1e-3, stats.gemm_ms * 1e-3, t3 - t2, now_seconds() - t3);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -310,6 +310,8 @@ private:
     std::map<std::vector<int64_t>, RecursionGraph> graph_cache;
     int persist_mode = 1;            // PBK_PERSIST=0: no persistent single-launch recursion for small systems
     DevBuf persist_table, persist_barrier;
+    DevBuf kubo_l, kubo_r, kubo_ws;   // Kubo-Bastin stacks and split-K workspace, kept between conductivity calls
+    bool keep_kubo_buffers = false;
     int graph_mode = 1;
     double graph_max_bytes = 64e6;   // vector block size up to which a recursion counts as launch-bound
     void clear_graphs();

@@ -488,9 +488,14 @@ ResGeometry res_geometry(int dtype, int k, int lanes, int ctas_per_sm, int stage
     uint32_t const stage_bytes = (rpb * (g.row_bytes + g.cb + g.kvb) + 127u) / 128u * 128u;
     // shared memory of one SM (227 KB opt-in, 1 KB reserved per CTA) shared by the resident CTAs; finish_sums holds 2 KB statically
     uint32_t const per_cta = (227u * 1024u) / static_cast<uint32_t>(g.ctas_per_sm) - 1024u - 2304u;
-    uint32_t const fixed = g.stages * stage_bytes + 16u * g.stages + 16u + 16u * RES_DESC_CAP;
-    g.xs_bytes = per_cta > fixed + 4096u ? (per_cta - fixed) / static_cast<uint32_t>(g.buffers) / 128u * 128u : 0u;
-    g.cap_rows = g.row_bytes ? static_cast<int>(g.xs_bytes / g.row_bytes) : 0;
+    // the ring gives way to the resident rows: wide matrix records (large k, 16-byte scalars) fall back to a shallower ring
+    // rather than leaving no room for a tile
+    for (;; --g.stages) {
+        uint32_t const fixed = g.stages * stage_bytes + 16u * g.stages + 16u + 16u * RES_DESC_CAP;
+        g.xs_bytes = per_cta > fixed + 4096u ? (per_cta - fixed) / static_cast<uint32_t>(g.buffers) / 128u * 128u : 0u;
+        g.cap_rows = g.row_bytes ? static_cast<int>(g.xs_bytes / g.row_bytes) : 0;
+        if (g.stages == 2 || g.cap_rows >= 4 * static_cast<int>(rpb)) break;
+    }
     if (g.cap_rows > 65535) { g.cap_rows = 65535; }     // 16-bit local codes
     g.rows_per_iteration = static_cast<int>(rpb);
     return g;

@@ -23,7 +23,7 @@
 //   Im(mu) = A'' * B'^T                     with A'' = [.. ai_k, -ar_k ..]   (pair swap + negate on fragment load)
 //
 // Kernel: 128 x 128 tile per CTA; 8 warps (4 x 2, warp tile 32 x 64 = 32 DMMAs per k4-step out of 12 fragment loads);
-// lane 0 of warp 0 issues the two bulk copies of a stage.  Three stages; full / empty mbarriers per stage, so the warps
+// lane 0 of warp 0 issues the bulk copies of a stage.  Three stages; full / empty mbarriers per stage, so the warps
 // never meet at a CTA barrier and may drift a stage apart (tools/probe/gemm_loop_probe.cu: this main loop sustains
 // 36.9 TFLOP/s from shared memory).  M is rarely a multiple of the tile (the
 // reference's num_moments is 4k+2): edge tiles copy only their valid rows, warps whose 32 x 64 region lies outside the
@@ -66,7 +66,7 @@ __device__ __forceinline__ double lds_as_double(uint32_t addr, float) { float v;
 /// grid has t x t tiles; the CTAs of the last tile row (column) also compute the `fold` remaining rows (columns).
 template<class Real, bool IMAG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) kubo_gemm_kernel(const unsigned char* __restrict__ A, const unsigned char* __restrict__ B, int M,
-                                                                    int64_t nblk, int64_t bs, double* __restrict__ part, int Mp, int64_t bpc, int fold) {
+                                                                    int64_t nblk, int64_t bs, double* __restrict__ part, int Mp, int64_t bpc, int fold, int chunk_rows) {
     using G = Geom<Real>;
     constexpr int ES = sizeof(Real);
     extern __shared__ __align__(128) unsigned char gemm_smem[];
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) kubo_gemm_kernel(const unsign
     int const active_m = (rows_a + 31) / 32, active_n = (rows_b + 63) / 64;                // consumer warps with work: wm < active_m, wn < active_n
 
     if (tid == 0) {
-        for (int st = 0; st < GEMM_STAGES; ++st) { mbar_init(full0 + 8 * st, 1u); mbar_init(empty0 + 8 * st, static_cast<uint32_t>(active_m * active_n)); }
+        for (int st = 0; st < GEMM_STAGES; ++st) { mbar_init(full0 + 8 * st, 1u); mbar_init(empty0 + 8 * st, static_cast<uint32_t>(32 * active_m * active_n)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) kubo_gemm_kernel(const unsign
     //      top of stage st, the slot that stage st - 1 occupied: the only wait in the CTA that involves all warps, and only
     //      warp 0 takes it (a dedicated producer warp would cap the kernel at 168 registers: 9 warps put 3 on one scheduler).
     uint32_t const bytes_a = static_cast<uint32_t>(rows_a + ext_a) * G::RS, bytes_b = static_cast<uint32_t>(rows_b + ext_b) * G::RS;
+    uint32_t const chunk = static_cast<uint32_t>(chunk_rows) * G::RS;
     const unsigned char* const pa0 = A + kb0 * bs + static_cast<int64_t>(m0) * G::RS;
     const unsigned char* const pb0 = B + kb0 * bs + static_cast<int64_t>(n0) * G::RS;
     auto produce = [&](int st) {       // stage st -> slot st % GEMM_STAGES
@@ -102,8 +103,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) kubo_gemm_kernel(const unsign
         if (round > 0) mbar_wait(empty0 + 8 * slot, static_cast<uint32_t>(round - 1) & 1u);
         uint32_t const dst = smem0 + slot * G::STAGE, bar = full0 + 8 * slot;
         mbar_expect_tx(bar, bytes_a + bytes_b);
-        bulk_g2s(dst, pa0 + st * bs, bytes_a, bar);
-        bulk_g2s(dst + G::TILE, pb0 + st * bs, bytes_b, bar);
+        // each operand tile in pieces of `chunk` bytes: several bulk copies in flight fetch a tile faster than one large
+        // copy does (matters for the light CTAs of edge tiles, which do little arithmetic per byte)
+        const unsigned char* const pa = pa0 + st * bs;
+        const unsigned char* const pb = pb0 + st * bs;
+        for (uint32_t o = 0; o < bytes_a; o += chunk) bulk_g2s(dst + o, pa + o, bytes_a - o < chunk ? bytes_a - o : chunk, bar);
+        for (uint32_t o = 0; o < bytes_b; o += chunk) bulk_g2s(dst + G::TILE + o, pb + o, bytes_b - o < chunk ? bytes_b - o : chunk, bar);
     };
     if (tid == 0) {
         for (int st = 0; st < GEMM_STAGES - 1 && st < nstage; ++st) produce(st);
@@ -176,7 +181,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) kubo_gemm_kernel(const unsign
                 }
                 if constexpr (EA && EB) { if (warp == 0) dmma_m8n8k4(ec[0], ec[1], ae, be); }
             }
-            release_stage(empty0 + 8 * slot, static_cast<uint32_t>(tid));   // proxy fence + one arrival per warp
+            // hand the stage back: every lane orders its own reads before the refill (proxy fence) and arrives itself, so
+            // the reader -> producer edge does not pass through another lane (compute-sanitizer's racecheck follows it)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(empty0 + 8 * slot);
             if (++slot == GEMM_STAGES) { slot = 0; ++round; }
         }
     };
@@ -260,13 +268,15 @@ cudaError_t gemm_t(const void* A, const void* B, int M, int64_t nblk, bool cplx,
         raised = true;
     }
     dim3 const grid(tiles, tiles, ksplit);
+    int chunk_rows = 256;  // rows per bulk copy: one copy per operand tile (experiment knob PBK_KUBO_CHUNK; pieces of 32 rows measured 5 % slower)
+    { char const* v = std::getenv("PBK_KUBO_CHUNK"); if (v && std::atoi(v) > 0) chunk_rows = std::atoi(v); }
     int64_t const bs = static_cast<int64_t>(M) * G::RS;
     auto const* a = static_cast<const unsigned char*>(A);
     auto const* b = static_cast<const unsigned char*>(B);
-    k_re<<<grid, GEMM_THREADS, G::SMEM, s>>>(a, b, M, nblk, bs, workspace, Mp, bpc, fold);
+    k_re<<<grid, GEMM_THREADS, G::SMEM, s>>>(a, b, M, nblk, bs, workspace, Mp, bpc, fold, chunk_rows);
     kubo_reduce_kernel<<<(M * M + 255) / 256, 256, 0, s>>>(workspace, ksplit, Mp, M, C, 0);
     if (cplx) {
-        k_im<<<grid, GEMM_THREADS, G::SMEM, s>>>(a, b, M, nblk, bs, workspace, Mp, bpc, fold);
+        k_im<<<grid, GEMM_THREADS, G::SMEM, s>>>(a, b, M, nblk, bs, workspace, Mp, bpc, fold, chunk_rows);
         kubo_reduce_kernel<<<(M * M + 255) / 256, 256, 0, s>>>(workspace, ksplit, Mp, M, C, 1);
     }
     return cudaGetLastError();

@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import pybinding_b200 as pb
 def run(env, fn):
-    for k in ("PBK_BULK", "PBK_GRAPH", "PBK_CONE", "PBK_DEVBUILD"): os.environ.pop(k, None)
+    for k in [k for k in os.environ if k.startswith("PBK_")]: os.environ.pop(k, None)
     os.environ.update(env)
     return fn()
 m32 = pb.graphene_rectangle(12.0, dtype=np.complex64, magnetic_field=300.0)
@@ -32,4 +32,9 @@ l1 = k.impl.moments_ldos(66, [fn([0, 0])])
 l2 = k.impl.moments_ldos(18, [fn([0, 0]), fn([3, 3]), fn([-4, 2])])
 gr = k.impl.moments_greens(34, fn([0, 0]), [fn([1, 1]), fn([2, -2])])
 ku = k.impl.moments_kubo(18, m64.system.x, m64.system.y, 2)
+ku2 = k.impl.moments_kubo(134, m64.system.x, m64.system.x, 1)   # 128 + 6: remainder rows folded into the last tile of the GEMM
+# resident-tile kernel (forced: the small lattice would not choose it), 16 float lanes = one 64-byte row
+r1 = run({"PBK_RES": "2", "PBK_RES_TILE": "128"}, lambda: dos(cub, (-8.2, 8.2), 34, 16))
+r0 = run({"PBK_RES": "0"}, lambda: dos(cub, (-8.2, 8.2), 34, 16))
+print("resident vs staged diff", float(abs(r1 - r0).max() / abs(r0).max()))
 print("staged vs general diff", float(abs(a - b).max() / abs(a).max()), "ok")
