@@ -101,20 +101,27 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    // The descriptors of the tiles this CTA will work on (tile blockIdx.x + i gridDim.x is its i-th) are copied to shared
-    // memory once: producer and consumers then read them with ld.shared instead of waiting for a global load at every
-    // tile switch (8 % of the stall samples in profiles/r02_ncu_cubic_res_r16_v2.csv).  The launcher sizes the grid so
-    // that RES_DESC_CAP descriptors cover the CTA's share.
-    for (uint32_t i = tid; i < RES_DESC_CAP; i += TPB) {
-        int64_t const t = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x;
-        if (t < a.ntiles) {
-            int4 const d = __ldg(reinterpret_cast<const int4*>(a.tiles) + t);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc0 + 16u * i), "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w) : "memory");
+    // The descriptors of the tiles this CTA works on (tile blockIdx.x + i gridDim.x is its i-th) are kept in shared memory,
+    // a window of RES_DESC_CAP at a time: producer and consumers read them with ld.shared instead of waiting for a global
+    // load at every tile switch (8 % of the stall samples in profiles/r02_ncu_cubic_res_r16_v2.csv).  Look-ups past the
+    // window (the producer and the tile prefetch run a little ahead of the consumers) go to global memory.
+    uint32_t dbase = 0;
+    auto load_window = [&](uint32_t first) {
+        for (uint32_t i = tid; i < RES_DESC_CAP; i += TPB) {
+            int64_t const t = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(first + i) * gridDim.x;
+            if (t < a.ntiles) {
+                int4 const d = __ldg(reinterpret_cast<const int4*>(a.tiles) + t);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc0 + 16u * i), "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w) : "memory");
+            }
         }
-    }
+    };
+    load_window(0u);
     __syncthreads();
     auto tile_desc = [&](uint32_t i) {   // descriptor of this CTA's i-th tile
-        uint4 const d = lds_u4(desc0 + 16u * i);
+        uint4 d;
+        if (i - dbase < RES_DESC_CAP) d = lds_u4(desc0 + 16u * (i - dbase));
+        else { int4 const g = __ldg(reinterpret_cast<const int4*>(a.tiles) + (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x));
+               d = make_uint4(static_cast<uint32_t>(g.x), static_cast<uint32_t>(g.y), static_cast<uint32_t>(g.z), static_cast<uint32_t>(g.w)); }
         return ResTile{static_cast<int32_t>(d.x), static_cast<int32_t>(d.y), static_cast<int32_t>(d.z), static_cast<int32_t>(d.w)};
     };
     uint32_t const my_tiles = static_cast<int>(blockIdx.x) < a.ntiles ? (static_cast<uint32_t>(a.ntiles) - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
     // the bulk copy: the phase completes exactly when everything has landed, no CTA barrier between issue and use.
     // The tile descriptor and the thread's first halo row numbers are fetched one tile ahead (`prefetch_tile`), so that
     // nothing waits for a global load when the copies are issued.
-    constexpr uint32_t HPT = 6;                            // halo rows per thread held in registers (more: loaded late)
+    constexpr uint32_t HPT = 5;                            // halo rows per thread held in registers (more: loaded late)
     ResTile nxt{0, 0, 0, 0};
     int32_t hidx[HPT];
     auto prefetch_tile = [&](uint32_t i) {
@@ -211,6 +218,12 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
     if (NB == 2u && my_tiles > 1u) { prefetch_tile(1u); issue_tile(1u); }
 
     for (uint32_t it = 0; it < my_tiles; ++it) {
+        if (it == dbase + RES_DESC_CAP) {   // next window of descriptors (every thread is here: the loop is CTA-uniform)
+            __syncthreads();
+            load_window(it);
+            __syncthreads();
+            dbase = it;
+        }
         ResTile const tl = tile_desc(it);
         uint32_t const nrows = static_cast<uint32_t>(tl.nrows);
         uint32_t const b = NB == 2u ? (it & 1u) : 0u;
@@ -457,7 +470,6 @@ cudaError_t launch_res_t(ResArgs const& a, int num_sms, cudaStream_t stream, Lau
     int grid = num_sms * a.geo.ctas_per_sm;
     if (grid > a.ntiles) grid = a.ntiles;
     if (grid > max_step_blocks(num_sms)) grid = max_step_blocks(num_sms);
-    if (static_cast<int64_t>(grid) * RES_DESC_CAP < a.ntiles) return cudaSuccess;   // more tiles per CTA than its descriptor cache holds
     ResDev d{};
     d.tiles = a.tiles; d.ntiles = a.ntiles; d.halo_rows = a.halo_rows;
     d.codes = static_cast<const unsigned char*>(a.codes); d.vals = static_cast<const unsigned char*>(a.vals);

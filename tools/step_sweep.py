@@ -45,19 +45,23 @@ def main():
         kpm = pb.kpm(model, energy_range=w["energy_range"], silent=True, max_batch=max_batch)
         mom = None
         best = None
+        sampler = bench.ClockSampler(0)
+        sampler.start()
         for _ in range(args.reps + 1):
             mom = kpm.impl.moments_dos(args.moments, R)
             s = kpm.stats
             steps = s.step_launches
             ms = s.step_ms / steps
             best = ms if best is None else min(best, ms)
+        clocks = sampler.stop()
         gbs = s.step_bytes / steps / (best * 1e-3) / 1e9
         if ref is None:
             ref = mom
         err = float(np.abs(mom - ref).max() / np.abs(ref).max())
         print(json.dumps(dict(config=cfg, ms_per_step=round(best, 4), vectors_per_ms=round(s.batch / best, 2), algorithmic_gbs=round(gbs, 1),
                               frac=round(gbs / peak, 4), hamiltonian_s=round(s.hamiltonian_time, 2),
-                              starter_ms=round(s.starter_ms, 1), batch=s.batch, rel_diff_vs_first=err,
+                              starter_ms=round(s.starter_ms, 1), batch=s.batch, rel_diff_vs_first=err, sm_mhz=clocks.get("sm_mhz"),
+                              power_w=clocks.get("power_w"), res_launches=int(s.res_launches), bulk_launches=int(s.bulk_launches),
                               total_s=round(time.time() - t0, 1))), flush=True)
         del kpm
 
