@@ -98,6 +98,38 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def snapshot(self):
+        """One sample, synchronously.  Every nvidia-smi query stalls the GPU's launch path for a moment: polled at 5 Hz
+        that doubles the duration of launch-bound steps (configs[0]: 1.5 ms per moments phase without the poll, 2.4 - 4.8 ms
+        with it, profiles/r02_bench_40nm_variance.log) while a 12 s step does not notice.  Timed regions shorter than two
+        seconds are therefore bracketed by one sample before and one after instead of being polled."""
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=20).stdout
+            for line in out.splitlines():
+                if line.strip():
+                    self.lines.append((time.perf_counter(), line.strip()))
+            self.bracket = True
+        except (OSError, subprocess.SubprocessError):
+            pass
+
+    def begin_region(self, expected_seconds):
+        """Call right before the timed region: polls when the region is long enough not to notice, brackets it otherwise."""
+        if expected_seconds >= 2.0:
+            self.start()
+            time.sleep(0.8)          # nvidia-smi's start-up stalls driver calls of this process: let it pass
+            self.mark_begin()
+        else:
+            self.mark_begin()
+            self.snapshot()
+
+    def end_region(self):
+        if self.proc is None and getattr(self, "bracket", False):
+            self.snapshot()
+            return self._summary(dict(note="timed region shorter than 2 s: bracketed by one sample before and one after "
+                                           "(polling nvidia-smi perturbs launch-bound steps)"))
+        return self.stop()
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append((time.perf_counter(), line.strip()))
@@ -110,6 +142,9 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        return self._summary({})
+
+    def _summary(self, extra):
         sm, mx, mem, power, reasons = [], [], [], [], set()
         lines = [(t, l) for t, l in self.lines if t >= self.begin]
         nearest = not lines and bool(self.lines)
@@ -136,7 +171,8 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(busy)) if busy else None, sm_max_mhz=max(mx) if mx else None,
                     reasons=sorted(reasons), samples=0 if nearest else len(sm), mem_mhz=float(np.median(mem)) if mem else None,
                     power_w=float(np.median(power)) if power else None,
-                    **(dict(note="timed region shorter than the 200 ms sampling period: the last sample before it is reported") if nearest else {}))
+                    **(dict(note="timed region shorter than the 200 ms sampling period: the last sample before it is reported") if nearest else {}),
+                    **extra)
 
 
 def sustained_copy(device, seconds=4.0):
@@ -371,13 +407,15 @@ def run_quantity(args, name, w):
         sys.stderr.write("bench.py: PARITY FAILED for {}: {}\n".format(name, parity))
         emit(dict(metric=metric, value=None, error="parity failed", parity=parity))
         sys.exit(1)
-    sampler.start()
+    t_warm = 0.0
     for _ in range(max(args.warmup, 1)):
+        t0 = time.perf_counter()
         call()
+        t_warm = time.perf_counter() - t0
     if q == "conductivity":
         gemm.update(ms=0.0, flops=0.0, step_ms=0.0)
     times, dev_ms, launches = [], [], 0
-    sampler.mark_begin()
+    sampler.begin_region(t_warm * args.steps)
     for _ in range(args.steps):
         t0 = time.perf_counter()
         out = call()
@@ -385,7 +423,7 @@ def run_quantity(args, name, w):
         st = kpm.stats
         dev_ms.append(st.moments_device_ms)
         launches += st.kernel_launches
-    clocks = sampler.stop()
+    clocks = sampler.end_region()
     st = kpm.stats
     t = float(np.mean(times))
     peak, peak_src = measured_peak()
@@ -502,13 +540,15 @@ def main():
     # ---- device-resident timing: Hamiltonian already in HBM, one step = the whole moments phase ----
     moments = None
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    t_warm = 0.0
     for _ in range(args.warmup):
+        t0 = time.perf_counter()
         moments = kpm.impl.moments_dos(M, R)
+        t_warm = time.perf_counter() - t0
     step_times, wall_times, launches, step_ms, step_bytes, step_launches, starter_ms, bulk_launches = [], [], 0, 0.0, 0.0, 0, 0.0, 0
     res_launches, persist_launches = 0, 0
     barrier()
-    sampler.mark_begin()
+    sampler.begin_region(max_over_ranks(t_warm) * args.steps if args.warmup else 10.0)
     for _ in range(args.steps):
         barrier()
         t0 = time.perf_counter()
@@ -527,7 +567,7 @@ def main():
         persist_launches += s.persist_launches
         starter_ms += s.starter_ms
         batch = s.batch
-    clocks = sampler.stop()
+    clocks = sampler.end_region()
     t_step = float(np.mean(step_times))
     value = nnz * M * R / t_step
     parity = oracle.check(moments, w["dtype"]) if oracle else None   # joins the oracle thread before the e2e leg
@@ -576,6 +616,7 @@ def main():
         del k2
         e2e = dict(value=nnz * M * R / float(np.mean(times)), unit=UNIT, h2d_bytes_per_step=int(h2d),
                    d2h_bytes_per_step=int(d2h), seconds=float(np.mean(times)), set_model_seconds=float(np.mean(set_times)),
+                   seconds_each=[round(x, 4) for x in times], set_model_seconds_each=[round(x, 4) for x in set_times],
                    note="kpm.model = model (host CSR mirrored into page-locked memory and uploaded, locality ordering on rank 0 + "
                         "broadcast) + calc_dos (scale / relabel / ELL / packing on the device, moments, allreduce, reconstruction, "
                         "D2H) through the public API")

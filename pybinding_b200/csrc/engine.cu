@@ -110,8 +110,9 @@ static int host_threads() {
     return std::max(1, std::min(nt, 16));
 }
 
-template<class F> static void parallel_rows(int64_t n, F fn, int64_t min_items = int64_t{1} << 16) {
+template<class F> static void parallel_rows(int64_t n, F fn, int64_t min_items = int64_t{1} << 16, int max_threads = 0) {
     int nt = host_threads();
+    if (max_threads > 0) nt = std::min(nt, max_threads);
     if (n < min_items) nt = 1;
     if (nt == 1) { fn(int64_t{0}, n); return; }
     int64_t const chunk = (n + nt - 1) / nt;
@@ -335,11 +336,14 @@ void Engine::set_hamiltonian(int dt, int64_t n_, const int32_t* indptr, const in
     d_indptr.ensure(sizeof(int32_t) * (static_cast<size_t>(n) + 1));
     d_indices.ensure(sizeof(int32_t) * static_cast<size_t>(std::max<int64_t>(nnz, 1)));
     d_data.ensure(sz * static_cast<size_t>(std::max<int64_t>(nnz, 1)));
-    parallel_rows(n + 1, [&](int64_t b, int64_t e) { std::memcpy(h_indptr.data() + b, indptr + b, sizeof(int32_t) * static_cast<size_t>(e - b)); });
+    // several ranks share one host: a bandwidth-bound copy gains nothing from 16 threads per rank, and rank 0's ordering
+    // threads should not be time-sliced against 8 x 16 of them
+    int const mt = world > 1 ? 4 : 0;
+    parallel_rows(n + 1, [&](int64_t b, int64_t e) { std::memcpy(h_indptr.data() + b, indptr + b, sizeof(int32_t) * static_cast<size_t>(e - b)); }, int64_t{1} << 16, mt);
     PBK_CUDA(cudaMemcpyAsync(d_indptr.as(), h_indptr.data(), sizeof(int32_t) * (static_cast<size_t>(n) + 1), cudaMemcpyHostToDevice, stream));
-    parallel_rows(nnz, [&](int64_t b, int64_t e) { std::memcpy(h_indices.data() + b, indices + b, sizeof(int32_t) * static_cast<size_t>(e - b)); });
+    parallel_rows(nnz, [&](int64_t b, int64_t e) { std::memcpy(h_indices.data() + b, indices + b, sizeof(int32_t) * static_cast<size_t>(e - b)); }, int64_t{1} << 16, mt);
     PBK_CUDA(cudaMemcpyAsync(d_indices.as(), h_indices.data(), sizeof(int32_t) * static_cast<size_t>(nnz), cudaMemcpyHostToDevice, stream));
-    parallel_rows(nnz, [&](int64_t b, int64_t e) { std::memcpy(h_data.data() + b * sz, static_cast<const char*>(data) + b * sz, sz * static_cast<size_t>(e - b)); });
+    parallel_rows(nnz, [&](int64_t b, int64_t e) { std::memcpy(h_data.data() + b * sz, static_cast<const char*>(data) + b * sz, sz * static_cast<size_t>(e - b)); }, int64_t{1} << 16, mt);
     PBK_CUDA(cudaMemcpyAsync(d_data.as(), h_data.data(), sz * static_cast<size_t>(nnz), cudaMemcpyHostToDevice, stream));
     dev_csr = true;
     double const t_copy = now_seconds();

@@ -23,7 +23,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.complex64): 1e-5,
        np.dtype(np.float64): 1e-11, np.dtype(np.complex128): 1e-11}
-KNOBS = ("PBK_PERSIST", "PBK_RES", "PBK_RES_TILE", "PBK_RES_ROW", "PBK_RES_CTAS", "PBK_RES_STAGES", "PBK_RELEASE", "PBK_DEVBUILD", "PBK_BULK", "PBK_XS", "PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL",
+KNOBS = ("PBK_PERSIST", "PBK_RES", "PBK_RES_TILE", "PBK_RES_ROW", "PBK_RES_CTAS", "PBK_RES_STAGES", "PBK_RES_BUFS", "PBK_RES_L2PF", "PBK_KUBO_WAVES", "PBK_KUBO_CHUNK", "PBK_RELEASE", "PBK_DEVBUILD", "PBK_BULK", "PBK_XS", "PBK_TILE", "PBK_TPB", "PBK_BPSM", "PBK_PF", "PBK_PFMASK", "PBK_MT_SEQUENTIAL",
          "PBK_CONE",
          "PBK_GRAPH", "PBK_GRAPH_MAX_MB")
 
@@ -341,3 +341,38 @@ def test_persistent_kernel_matches_launch_per_step_and_oracle(dtype, k):
         huge = pb.graphene_rectangle(120.0, dtype=dtype)          # 550 k sites: too many rows for one resident grid
         _, sh = dos_moments(huge, er, 34, 1)
         assert sh.persist_launches == 0
+
+
+def test_resident_tile_kernel_with_more_tiles_than_the_descriptor_window():
+    """A CTA of `cheb_step_res` keeps a window of 128 tile descriptors in shared memory and reloads it as it goes; small
+    tiles on a system of 1.4 M sites give every CTA ~150 tiles, so the reload and the look-ups past the window (producer,
+    tile prefetch) are exercised.  Checked against the staged kernel on the same starters."""
+    model = pb.graphene_rectangle(190.0, dtype=np.float32, onsite=0.1)
+    er = (-9.0, 9.2)
+    M, R = 18, 16
+    staged, s0 = dos_moments(model, er, M, R, PBK_RES=0)
+    assert s0.res_launches == 0
+    res, s1 = dos_moments(model, er, M, R, PBK_RES=2, PBK_RES_TILE=64, PBK_RES_CTAS=1)
+    n = model.hamiltonian.shape[0]
+    assert n / 64 > 148 * 128, "the system is too small to overflow the descriptor window"
+    assert s1.res_launches == M // 2 - 1
+    assert rel_err(res, staged) < 1e-6
+    assert abs(res[0].real - n / 2) < 1e-6 * n
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex64], ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("M", [18, 128, 130, 134, 136, 200, 262])
+def test_kubo_gemm_tile_shapes(dtype, M):
+    """The Kubo-Bastin contraction (kubo.cu) for every tile situation of the 128 x 128 tiling: a single edge tile (18), one
+    full tile (128), remainders folded into the last tiles (130, 134, 262 = 2 x 128 + 6), a remainder that gets its own tile
+    row (136, 200) -- real and complex stacks, against the hp oracle."""
+    dtype = np.dtype(dtype)
+    model = pb.graphene_rectangle(6.0, dtype=dtype, onsite=0.2, magnetic_field=300.0 if dtype.kind == "c" else 0.0)
+    er = (-9.0, 9.4)
+    kpm = pb.kpm(model, energy_range=er, silent=True)
+    ref = OracleKPM(model.hamiltonian, energy_range=er, hp=True)
+    x, y = model.system.x, model.system.y
+    got = kpm.impl.moments_kubo(M, x, y, 3)          # three vectors: two lanes + a ragged one for f64, padded lanes for c64
+    expected = ref.kubo_moments(M, x, y, 3)
+    assert got.shape == (M, M)
+    assert rel_err(got, expected) < TOL[dtype] * 5
