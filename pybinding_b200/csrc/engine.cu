@@ -240,6 +240,7 @@ Engine::Engine(int device_, pbk_config const& cfg) : device(device_), config(cfg
     bcast_order = static_cast<int>(env_int("PBK_BCAST_ORDER", 1));
     macro_tiles = env_int("PBK_MACRO", 256);   // 65 k-site macro-blocks: +4 % on configs[1] in short runs, +1.5 % in the power-capped bench (profiles/r01_ab_order_v6.log)
     cone_mode = static_cast<int>(env_int("PBK_CONE", 1));
+    cone_group_cap = static_cast<int>(env_int("PBK_CONE_GROUP", 0));
     graph_mode = static_cast<int>(env_int("PBK_GRAPH", 1));
     persist_mode = static_cast<int>(env_int("PBK_PERSIST", 1));
     graph_max_bytes = 1e6 * static_cast<double>(env_int("PBK_GRAPH_MAX_MB", 64));
@@ -1735,6 +1736,7 @@ bool Engine::moments_ldos_cones(int M, Indices const& target, cd* out) {
     cudaMemGetInfo(&free_b, &total_b);
     double const budget = std::min(0.4 * static_cast<double>(free_b) + static_cast<double>(cone_val.bytes() + cone_col.bytes() + vec_a.bytes()), 16e9);
     int group = static_cast<int>(std::max(1.0, std::min(64.0, budget / (1.25 * slot_bytes(first_cone)))));
+    if (cone_group_cap > 0) group = std::min(group, cone_group_cap);
     group = std::max(1, std::min(group, count));
     int const nthreads = std::max(1, std::min<int>({static_cast<int>(std::thread::hardware_concurrency()), 16, group}));
     marks.resize(nthreads, std::vector<int32_t>(static_cast<size_t>(n), -1));

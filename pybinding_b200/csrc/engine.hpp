@@ -293,7 +293,8 @@ private:
     int64_t coarse_sites = 16;   // PBK_COARSE: consecutive sites per super-node of the macro-block pass (1: no coarsening)
     int64_t macro_tiles = 256;   // PBK_MACRO: tiles per macro-block of the two-level locality ordering (0: one level)
     bool identity_order = false; // PBK_IDENTITY_ORDER=1: tiles of consecutive rows in the caller's order instead of locality clusters
-    int cone_mode = 1;           // PBK_CONE=0: the previous host-side full BFS relabelling for LDOS
+    int cone_mode = 1;
+    int cone_group_cap = 0;              // PBK_CONE_GROUP: at most this many light-cone sub-systems per launch (0: bounded by memory only)           // PBK_CONE=0: the previous host-side full BFS relabelling for LDOS
     DevBuf vec_a, vec_b, vec_t, raw, mom, m01, acc, partials, counter, scratch, mt_state, mt_states, idx_buf;
     static constexpr int MT_MAX_SEGMENTS = 2048;
     uint64_t stream_pos = 0;     // next draw of the reference's random stream
