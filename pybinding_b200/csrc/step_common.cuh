@@ -130,16 +130,36 @@ __device__ __forceinline__ void finish_sums(StepDev const& a, double (&acc)[NACC
     int p2 = 1;
     while (p2 < rpb) p2 <<= 1;
     int const RC = a.R * C;
+    if (cpr >= 32 || 32 % cpr == 0) {
+        // rows that share a warp are folded with warp shuffles (fixed order), then thread tx adds the per-warp (per-row)
+        // partials of its column in warp order: two CTA barriers per accumulator instead of log2(rows) + 2
 #pragma unroll
-    for (int q = 0; q < NACC; ++q) {
-        sm[tid] = acc[q];
-        for (int s = p2 >> 1; s > 0; s >>= 1) {
+        for (int q = 0; q < NACC; ++q) {
+            double v = acc[q];                                     // threads without a row hold zeros
+            if (cpr < 32) { for (int off = 16; off >= cpr; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off); }
+            sm[tid] = v;
             __syncthreads();
-            if (ty < s && ty + s < rpb) sm[tid] += sm[tid + s * cpr];
+            if (tid < cpr) {
+                double s = 0.0;
+                if (cpr >= 32) { for (int r = 0; r < rpb; ++r) s += sm[tid + r * cpr]; }
+                else { for (int w = 0; w < TPB / 32; ++w) s += sm[w * 32 + tid]; }   // lane tx of every warp holds the warp's partial
+                a.partials[static_cast<int64_t>(blockIdx.x) * RC + tid * NACC + q] = s;
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        if (ty == 0) a.partials[static_cast<int64_t>(blockIdx.x) * RC + tx * NACC + q] = sm[tx];
-        __syncthreads();
+    } else {
+        // chunk counts that do not divide a warp (R = 12, 20, ...): shared-memory tree over the rows
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) {
+            sm[tid] = acc[q];
+            for (int s = p2 >> 1; s > 0; s >>= 1) {
+                __syncthreads();
+                if (ty < s && ty + s < rpb) sm[tid] += sm[tid + s * cpr];
+            }
+            __syncthreads();
+            if (ty == 0) a.partials[static_cast<int64_t>(blockIdx.x) * RC + tx * NACC + q] = sm[tx];
+            __syncthreads();
+        }
     }
     __threadfence();
     __syncthreads();
