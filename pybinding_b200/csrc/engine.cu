@@ -611,13 +611,16 @@ void cluster_order(int64_t n, const int32_t* indptr, const int32_t* indices, int
         cptr.resize_uninit(static_cast<size_t>(ns) + 1);
         cidx.resize_uninit(static_cast<size_t>(ns) * CAP);
         std::atomic<bool> overflow{false};
+        int cshift = -1;   // super-nodes of 2^cshift sites: a shift instead of a 64-bit division per matrix element
+        if ((coarse & (coarse - 1)) == 0) { cshift = 0; while ((int64_t{1} << cshift) < coarse) ++cshift; }
         parallel_rows(ns, [&](int64_t b, int64_t e) {
             for (int64_t sn = b; sn < e; ++sn) {
                 int32_t* const out = cidx.data() + sn * CAP;
                 int cnt = 0;
                 int64_t const lo = sn * coarse, hi = std::min<int64_t>(n, lo + coarse);
                 for (int p = indptr[lo]; p < indptr[hi]; ++p) {
-                    int32_t const c = static_cast<int32_t>(indices[p] / coarse);
+                    int32_t const c = cshift >= 0 ? static_cast<int32_t>(static_cast<uint32_t>(indices[p]) >> cshift)
+                                                  : static_cast<int32_t>(indices[p] / coarse);
                     if (c == sn) continue;
                     bool seen = false;
                     for (int q = 0; q < cnt; ++q) seen |= (out[q] == c);
