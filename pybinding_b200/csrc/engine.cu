@@ -38,13 +38,73 @@ void cuda_check(cudaError_t err, char const* what, char const* file, int line) {
     throw Error(PBK_CUDA_ERROR, buf);
 }
 
+namespace {
+struct DevBlockCache {
+    struct Block { int dev; void* ptr; size_t size; };
+    std::mutex mutex;
+    std::vector<Block> blocks;
+    size_t bytes = 0;
+    static constexpr size_t MIN_BLOCK = size_t{1} << 20, MAX_BYTES = size_t{12} << 30;
+};
+DevBlockCache& dev_cache() { static DevBlockCache c; return c; }
+} // anonymous namespace
+
+size_t DevBuf::cached_bytes() {
+    auto& c = dev_cache();
+    std::lock_guard<std::mutex> lock(c.mutex);
+    return c.bytes;
+}
+
+void DevBuf::flush_cache() {
+    auto& c = dev_cache();
+    std::vector<DevBlockCache::Block> blocks;
+    { std::lock_guard<std::mutex> lock(c.mutex); blocks.swap(c.blocks); c.bytes = 0; }
+    for (auto const& b : blocks) cudaFree(b.ptr);
+}
+
 void DevBuf::alloc(size_t bytes) {
     if (bytes == 0) bytes = 16;
-    PBK_CUDA(cudaMalloc(&ptr, bytes));
+    cudaGetDevice(&dev);
+    if (bytes >= DevBlockCache::MIN_BLOCK) {
+        auto& c = dev_cache();
+        std::lock_guard<std::mutex> lock(c.mutex);
+        for (size_t i = 0; i < c.blocks.size(); ++i) {
+            if (c.blocks[i].dev == dev && c.blocks[i].size == bytes) {
+                ptr = c.blocks[i].ptr; size = bytes;
+                c.bytes -= bytes;
+                c.blocks.erase(c.blocks.begin() + static_cast<std::ptrdiff_t>(i));
+                return;
+            }
+        }
+    }
+    cudaError_t err = cudaMalloc(&ptr, bytes);
+    if (err == cudaErrorMemoryAllocation) {   // give the cached blocks back and try once more
+        cudaGetLastError();
+        flush_cache();
+        err = cudaMalloc(&ptr, bytes);
+    }
+    if (err != cudaSuccess) ptr = nullptr;
+    PBK_CUDA(err);
     size = bytes;
 }
 void DevBuf::release() {
-    if (ptr) { cudaFree(ptr); ptr = nullptr; size = 0; }
+    if (!ptr) return;
+    auto& c = dev_cache();
+    bool cached = false;
+    if (size >= DevBlockCache::MIN_BLOCK && size <= DevBlockCache::MAX_BYTES / 2) {
+        cudaDeviceSynchronize();   // what cudaFree guarantees: nothing in flight still uses the block
+        std::lock_guard<std::mutex> lock(c.mutex);
+        while (!c.blocks.empty() && c.bytes + size > DevBlockCache::MAX_BYTES) {   // bounded: oldest blocks go first
+            cudaFree(c.blocks.front().ptr);
+            c.bytes -= c.blocks.front().size;
+            c.blocks.erase(c.blocks.begin());
+        }
+        c.blocks.push_back({dev, ptr, size});
+        c.bytes += size;
+        cached = true;
+    }
+    if (!cached) cudaFree(ptr);
+    ptr = nullptr; size = 0;
 }
 
 void* PinnedBuf::ensure(size_t bytes) {
@@ -1231,6 +1291,7 @@ int Engine::lane_pad(int R) const {
 int Engine::pick_batch(int vectors, int extra_blocks) const {
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
+    free_b += DevBuf::cached_bytes();   // blocks parked in the allocation cache are given back on demand
     // vec_a / vec_b (+ extra) blocks and the raw random words of one lane
     double const per_lane = static_cast<double>(n) * (dtype_size(dtype) * (2 + extra_blocks) + 4 * dtype_words(dtype));
     double const reusable = static_cast<double>(vec_a.bytes() + vec_b.bytes() + raw.bytes());
@@ -1737,6 +1798,7 @@ bool Engine::moments_ldos_cones(int M, Indices const& target, cd* out) {
     };
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
+    free_b += DevBuf::cached_bytes();   // blocks parked in the allocation cache are given back on demand
     double const budget = std::min(0.4 * static_cast<double>(free_b) + static_cast<double>(cone_val.bytes() + cone_col.bytes() + vec_a.bytes()), 16e9);
     int group = static_cast<int>(std::max(1.0, std::min(64.0, budget / (1.25 * slot_bytes(first_cone)))));
     if (cone_group_cap > 0) group = std::min(group, cone_group_cap);
@@ -2112,6 +2174,7 @@ void Engine::moments_kubo(int M, const float* left, const float* right, int num_
     // pass are bounded by the memory of the two stacks.
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
+    free_b += DevBuf::cached_bytes();   // blocks parked in the allocation cache are given back on demand
     KuboStackLayout const probe = kubo_stack_layout(dtype, M, 256);      // row stride (payload + pad) of this scalar type
     double const pad = static_cast<double>(probe.row_stride) / 256.0;
     double const per_lane = (2.0 * M * pad + 5.0) * static_cast<double>(n) * s + 8.0 * static_cast<double>(n);

@@ -9,6 +9,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <atomic>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -26,24 +27,31 @@ struct Error : std::runtime_error {
 void cuda_check(cudaError_t err, char const* what, char const* file, int line);
 #define PBK_CUDA(call) ::pbk::cuda_check((call), #call, __FILE__, __LINE__)
 
-/// RAII device allocation
+/// RAII device allocation.  Blocks of a megabyte or more go back to a small per-process cache instead of cudaFree (which
+/// unmaps the range under driver-wide locks: 0.1 - 0.5 s for the 3 GB of layouts that `set_hamiltonian` replaces when
+/// several ranks share a host) and are handed out again to requests of exactly the same size -- the pattern of
+/// re-setting a Hamiltonian of the same shape.  Release synchronises the device like cudaFree does; the cache is bounded,
+/// flushed when an allocation fails and when the last engine goes away.
 class DevBuf {
 public:
     DevBuf() = default;
     explicit DevBuf(size_t bytes) { alloc(bytes); }
     DevBuf(DevBuf const&) = delete;
     DevBuf& operator=(DevBuf const&) = delete;
-    DevBuf(DevBuf&& o) noexcept : ptr(o.ptr), size(o.size) { o.ptr = nullptr; o.size = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); ptr = o.ptr; size = o.size; o.ptr = nullptr; o.size = 0; } return *this; }
+    DevBuf(DevBuf&& o) noexcept : ptr(o.ptr), size(o.size), dev(o.dev) { o.ptr = nullptr; o.size = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); ptr = o.ptr; size = o.size; dev = o.dev; o.ptr = nullptr; o.size = 0; } return *this; }
     ~DevBuf() { release(); }
     void alloc(size_t bytes);
     void ensure(size_t bytes) { if (bytes > size) { release(); alloc(bytes); } }
     void release();
     template<class T = void> T* as() const { return static_cast<T*>(ptr); }
     size_t bytes() const { return size; }
+    static void flush_cache();   // cudaFree every cached block
+    static size_t cached_bytes();
 private:
     void* ptr = nullptr;
     size_t size = 0;
+    int dev = -1;
 };
 
 /// Host array without value-initialisation: large buffers are first touched by the (parallel) code that fills them
@@ -197,7 +205,18 @@ struct NcclApi {
 struct NcclId { char bytes[128]; };  // ncclUniqueId
 
 
+/// Declared first in Engine, hence destroyed last: when the last engine of the process is gone (its buffers have just been
+/// returned to the block cache) the cache is emptied.
+struct DevCacheGuard {
+    DevCacheGuard() { ++live(); }
+    ~DevCacheGuard() { if (--live() == 0) DevBuf::flush_cache(); }
+    DevCacheGuard(DevCacheGuard const&) = delete;
+    DevCacheGuard& operator=(DevCacheGuard const&) = delete;
+    static std::atomic<int>& live() { static std::atomic<int> n{0}; return n; }
+};
+
 class Engine {
+    DevCacheGuard cache_guard;
 public:
     Engine(int device, pbk_config const& config);
     ~Engine();
