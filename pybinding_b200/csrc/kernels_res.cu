@@ -35,7 +35,11 @@ namespace pbk {
 
 namespace {
 
-constexpr uint32_t RES_DESC_CAP = 128;   // tile descriptors a CTA keeps in shared memory (2 KB)
+#ifndef PBK_RES_HPT
+#define PBK_RES_HPT 5      // halo row numbers a thread holds in registers one tile ahead (6: 12 bytes of spills, 0.749 of the roofline on the cubic lattice; 5: 0.766; 4: 0.751)
+#endif
+constexpr uint32_t RES_DESC_WIN = 64;                  // tile descriptors per window
+constexpr uint32_t RES_DESC_CAP = 2 * RES_DESC_WIN;    // two windows in shared memory (2 KB)
 
 struct ResDev {  // kernel parameters
     const ResTile* tiles; int ntiles;
@@ -101,27 +105,25 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    // The descriptors of the tiles this CTA works on (tile blockIdx.x + i gridDim.x is its i-th) are kept in shared memory,
-    // a window of RES_DESC_CAP at a time: producer and consumers read them with ld.shared instead of waiting for a global
-    // load at every tile switch (8 % of the stall samples in profiles/r02_ncu_cubic_res_r16_v2.csv).  Look-ups past the
-    // window (the producer and the tile prefetch run a little ahead of the consumers) go to global memory.
-    uint32_t dbase = 0;
-    auto load_window = [&](uint32_t first) {
-        for (uint32_t i = tid; i < RES_DESC_CAP; i += TPB) {
+    // The descriptors of the tiles this CTA works on (tile blockIdx.x + i gridDim.x is its i-th) are kept in shared memory:
+    // producer and consumers read them with ld.shared instead of waiting for a global load at every tile switch (8 % of the
+    // stall samples in profiles/r02_ncu_cubic_res_r16_v2.csv).  Two windows of RES_DESC_WIN descriptors alternate: when the
+    // consumers enter window k, window k + 1 is loaded over window k - 1, so every look-up (the producer and the tile
+    // prefetch run a few tiles ahead) is a branch-free ld.shared at index i mod 2 RES_DESC_WIN.
+    auto load_window = [&](uint32_t first) {   // descriptors first .. first + RES_DESC_WIN - 1
+        for (uint32_t i = tid; i < RES_DESC_WIN; i += TPB) {
             int64_t const t = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(first + i) * gridDim.x;
             if (t < a.ntiles) {
                 int4 const d = __ldg(reinterpret_cast<const int4*>(a.tiles) + t);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc0 + 16u * i), "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc0 + 16u * ((first + i) & (RES_DESC_CAP - 1u))), "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w) : "memory");
             }
         }
     };
     load_window(0u);
+    load_window(RES_DESC_WIN);
     __syncthreads();
-    auto tile_desc = [&](uint32_t i) {   // descriptor of this CTA's i-th tile
-        uint4 d;
-        if (i - dbase < RES_DESC_CAP) d = lds_u4(desc0 + 16u * (i - dbase));
-        else { int4 const g = __ldg(reinterpret_cast<const int4*>(a.tiles) + (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x));
-               d = make_uint4(static_cast<uint32_t>(g.x), static_cast<uint32_t>(g.y), static_cast<uint32_t>(g.z), static_cast<uint32_t>(g.w)); }
+    auto tile_desc = [&](uint32_t i) {   // descriptor of this CTA's i-th tile (i within the two resident windows)
+        uint4 const d = lds_u4(desc0 + 16u * (i & (RES_DESC_CAP - 1u)));
         return ResTile{static_cast<int32_t>(d.x), static_cast<int32_t>(d.y), static_cast<int32_t>(d.z), static_cast<int32_t>(d.w)};
     };
     uint32_t const my_tiles = static_cast<int>(blockIdx.x) < a.ntiles ? (static_cast<uint32_t>(a.ntiles) - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
     // the bulk copy: the phase completes exactly when everything has landed, no CTA barrier between issue and use.
     // The tile descriptor and the thread's first halo row numbers are fetched one tile ahead (`prefetch_tile`), so that
     // nothing waits for a global load when the copies are issued.
-    constexpr uint32_t HPT = 5;                            // halo rows per thread held in registers (more: loaded late)
+    constexpr uint32_t HPT = PBK_RES_HPT;                            // halo rows per thread held in registers (more: loaded late)
     ResTile nxt{0, 0, 0, 0};
     int32_t hidx[HPT];
     auto prefetch_tile = [&](uint32_t i) {
@@ -218,12 +220,9 @@ __global__ void __launch_bounds__(TPB, MINB) cheb_step_res(ResDev a) {
     if (NB == 2u && my_tiles > 1u) { prefetch_tile(1u); issue_tile(1u); }
 
     for (uint32_t it = 0; it < my_tiles; ++it) {
-        if (it == dbase + RES_DESC_CAP) {   // next window of descriptors (every thread is here: the loop is CTA-uniform)
-            __syncthreads();
-            load_window(it);
-            __syncthreads();
-            dbase = it;
-        }
+        // entering a new window: the one after it replaces the one just left (nobody reads that any more; the stores are
+        // published by the CTA barrier at the end of this tile, long before the first look-up into the new window)
+        if (it != 0u && (it & (RES_DESC_WIN - 1u)) == 0u) load_window(it + RES_DESC_WIN);
         ResTile const tl = tile_desc(it);
         uint32_t const nrows = static_cast<uint32_t>(tl.nrows);
         uint32_t const b = NB == 2u ? (it & 1u) : 0u;
