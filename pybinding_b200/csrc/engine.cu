@@ -92,7 +92,11 @@ void DevBuf::release() {
     auto& c = dev_cache();
     bool cached = false;
     if (size >= DevBlockCache::MIN_BLOCK && size <= DevBlockCache::MAX_BYTES / 2) {
+        int cur = dev;
+        cudaGetDevice(&cur);
+        if (cur != dev) cudaSetDevice(dev);
         cudaDeviceSynchronize();   // what cudaFree guarantees: nothing in flight still uses the block
+        if (cur != dev) cudaSetDevice(cur);
         std::lock_guard<std::mutex> lock(c.mutex);
         while (!c.blocks.empty() && c.bytes + size > DevBlockCache::MAX_BYTES) {   // bounded: oldest blocks go first
             cudaFree(c.blocks.front().ptr);
