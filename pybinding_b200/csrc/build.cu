@@ -82,6 +82,7 @@ __global__ void invert_order_kernel(const int32_t* __restrict__ queue, int64_t n
     if (i < n) perm[queue[i]] = static_cast<int32_t>(i);
 }
 
+#pragma nv_diag_suppress 549   // "c is used before its value is set": the insertion sort only reads entries it has written
 template<class T>
 __global__ void __launch_bounds__(128) csr_to_ell_kernel(BuildArgs a, const T* __restrict__ data, T* __restrict__ val) {
     using R = typename Ops<T>::R;
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(128) csr_to_ell_kernel(BuildArgs a, const T* _
     int64_t const row = reordered ? a.queue[new_row] : new_row;
     R const f = static_cast<R>(a.f), sb = static_cast<R>(a.sb);
     bool const offset = a.mode == BUILD_SCALED && sb != R{0};
-    int32_t c[BUILD_KMAX]; T v[BUILD_KMAX];
+    int32_t c[BUILD_KMAX]; T v[BUILD_KMAX];   // filled from the front by `insert`; entry j - 1 is read only when j > 0
     int cnt = 0;
     bool diag_done = !offset;
     auto insert = [&](int32_t cc, T vv) {   // insertion sort by new column (rows are short)
